@@ -1,0 +1,180 @@
+/*
+ * renet_b200.h -- C-ABI of librenet_b200.so: the B200 (sm_100a) kernels behind RE-Net's
+ * RGCN-aggregate + GRU hot path.
+ *
+ * The reference (INK-USC/RE-Net) is pure Python and has no FFI of its own; the entry points below
+ * are what a binding for this path would bind -- one per arithmetic step the reference dispatches
+ * to PyTorch/DGL library kernels.  Each declaration cites the
+ * reference code it replaces (file:line under the reference tree).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - the caller owns every buffer; nothing is allocated, freed or retained by the library;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *     no hidden synchronisation, safe to capture in a CUDA graph, re-entrant, stateless;
+ *   - fp32 features/weights, int32 indices (the reference uses int64; convert at the boundary);
+ *   - return 0 on success, a negative renet_status otherwise; renet_last_error() (thread-local)
+ *     describes the failure.  No exceptions, no exit().
+ */
+#ifndef RENET_B200_H
+#define RENET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  RENET_OK = 0,
+  RENET_ERR_INVALID_ARG = -1,   /* bad shape / null pointer / unsupported configuration        */
+  RENET_ERR_CUDA = -2,          /* a CUDA runtime call or kernel launch failed                   */
+  RENET_ERR_NO_DEVICE = -3      /* no sm_100 device visible                                      */
+} renet_status;
+
+/* Library version (major*10000 + minor*100 + patch). */
+int renet_version(void);
+/* Message for the last non-zero status returned on this thread ("" if none). */
+const char* renet_last_error(void);
+/* Number of kernels this library has launched on this process so far (for bench.py's
+ * "gpu_launches" claim). */
+int64_t renet_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph preprocessing.  Replaces what DGL does inside g.update_all (RGCN.py:91) to find the
+ * in-edges of every node: turns the COO edge list of the batched history graph (dgl.batch,
+ * utils.py:238) into CSR by destination.  Stable: edges of one destination keep their COO order.
+ *   dst/src/etype [E] -> row_ptr [N+1], col_src [E], col_type [E], perm [E] (CSR slot -> COO edge,
+ *   may be NULL).  workspace: at least renet_csr_workspace_bytes(N, E) bytes.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t renet_csr_workspace_bytes(int64_t N, int64_t E);
+int renet_build_csr(const int32_t* dst, const int32_t* src, const int32_t* etype,
+                    int64_t N, int64_t E,
+                    int32_t* row_ptr, int32_t* col_src, int32_t* col_type, int32_t* perm,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * RGCN block-diagonal layer, forward.
+ * Replaces RGCNLayer.forward + RGCNBlockLayer.{msg_func,propagate,apply_func}
+ * (RGCN.py:33-51, 79-94) and, through h_index, the embedding lookup ndata['h'] = ent_embeds[id]
+ * (utils.py:239):
+ *
+ *   Hout[v] = act( norm[v] * sum_{e: dst(e)=v} blockdiag(W[col_type[e]]) . Hin[col_src[e]]
+ *                  + Hin[v] @ Wloop )              with  Hin[v] = H[h_index ? h_index[v] : v]
+ *
+ *   H        [*, d_in]  row-major fp32 (rows addressed through h_index when given)
+ *   h_index  [N] or NULL
+ *   W        [R2, num_bases*(d_in/num_bases)*(d_out/num_bases)]  (RGCN.py:75-77 layout:
+ *            block b, input i, output j at  b*si*so + i*so + j)
+ *   Wloop    [d_in, d_out] or NULL (self_loop=False)
+ *   row_ptr/col_src/col_type : CSR by destination (renet_build_csr); col_type already holds the
+ *            column the reference selects with `reverse` (type_o if reverse else type_s,
+ *            RGCN.py:80-85)
+ *   norm     [N]   (1/in-degree of the batched sub-graphs, utils.py:126-127)
+ *   Hout     [N, d_out]
+ *   relu     1 = F.relu (layer 1), 0 = identity (layer 2)  (Aggregator.py:119-122)
+ * E == 0 follows DGL 0.4: the reduce is skipped and only the apply UDF runs (agg = Hin; needs
+ * d_in == d_out).  Dropout is not applied here (p = 0 / eval).
+ * ---------------------------------------------------------------------------------------------- */
+int renet_rgcn_block_fwd(const float* H, const int32_t* h_index,
+                         const float* W, const float* Wloop,
+                         const int32_t* row_ptr, const int32_t* col_src, const int32_t* col_type,
+                         const float* norm, float* Hout,
+                         int64_t N, int64_t E, int32_t d_in, int32_t d_out,
+                         int32_t num_bases, int32_t R2, int32_t relu, void* stream);
+
+/* The two halves of the layer, exposed separately for profiling / tests:
+ *   renet_selfloop_gemm : Hout = Hin @ Wloop                       (RGCN.py:35)
+ *   renet_rgcn_gather   : Hout = act(norm * agg + (has_loop ? Hout : 0))   (RGCN.py:79-94, 45-48) */
+int renet_selfloop_gemm(const float* H, const int32_t* h_index, const float* Wloop, float* Hout,
+                        int64_t N, int32_t d_in, int32_t d_out, void* stream);
+int renet_rgcn_gather(const float* H, const int32_t* h_index, const float* W,
+                      const int32_t* row_ptr, const int32_t* col_src, const int32_t* col_type,
+                      const float* norm, float* Hout,
+                      int64_t N, int64_t E, int32_t d_in, int32_t d_out,
+                      int32_t num_bases, int32_t R2, int32_t relu, int32_t has_loop, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * RGCN block-diagonal layer, backward (autograd of the above; the reference relies on
+ * torch.autograd through bmm / index_select / DGL's reduce, train.py:139).
+ *
+ *   G = dHout * (relu ? Hout > 0 : 1)
+ *   dHin[u]  += sum_{e: src(e)=u} blockdiag(W[type_e])^T . (norm[dst_e] * G[dst_e])  +  G[u] @ Wloop^T
+ *   dW[r]    += sum_{e: type_e=r} Hin[src_e] (x) (norm[dst_e] * G[dst_e])     (per 2x2 block)
+ *   dWloop   += Hin^T @ G
+ *
+ *   t_row_ptr/t_col_dst/t_col_type : CSR by SOURCE (renet_build_csr with src/dst swapped)
+ *   rel_ptr [R2+1], rel_src/rel_dst [E] : edges grouped by type (renet_build_csr keyed on etype)
+ *   dH       [N, d_in]   written (not accumulated); when h_index is given the caller scatters it
+ *            into d(ent_embeds) with renet_scatter_add_rows
+ *   dW       [R2, ...]   ACCUMULATED (+=)  -- both layers / both directions add into .grad
+ *   dWloop   [d_in,d_out] ACCUMULATED (+=)
+ *   G_ws     workspace of N*d_out (rounded up to a multiple of 4) + d_in*d_out floats; on return its
+ *            first N*d_out floats hold P = dHout * act'(Hout)
+ * ---------------------------------------------------------------------------------------------- */
+int renet_rgcn_block_bwd(const float* H, const int32_t* h_index,
+                         const float* W, const float* Wloop,
+                         const int32_t* t_row_ptr, const int32_t* t_col_dst, const int32_t* t_col_type,
+                         const int32_t* rel_ptr, const int32_t* rel_src, const int32_t* rel_dst,
+                         const float* norm, const float* Hout, const float* dHout,
+                         float* dH, float* dW, float* dWloop, float* G_ws,
+                         int64_t N, int64_t E, int32_t d_in, int32_t d_out,
+                         int32_t num_bases, int32_t R2, int32_t relu, void* stream);
+
+/* Backward of renet_selfloop_gemm:  dH = dLoop @ Wloop^T  (written),  dWloop += Hin^T @ dLoop.
+ * ws: d_in*d_out floats. */
+int renet_selfloop_gemm_bwd(const float* H, const int32_t* h_index, const float* Wloop,
+                            const float* dLoop, float* dH, float* dWloop, float* ws,
+                            int64_t N, int32_t d_in, int32_t d_out, void* stream);
+
+/* dst[index[i], :] += src[i, :]   (gradient of the embedding lookup utils.py:239, and of the
+ * read-out gather Aggregator.py:140).  d % 4 == 0. */
+int renet_scatter_add_rows(const float* src, const int32_t* index, float* dst,
+                           int64_t n_rows, int32_t d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Read-out + concat + GRU, forward.  Replaces Aggregator.py:139-165 (gather of the read-out rows,
+ * the "# Slow!!!" concat loop, zero padding, pack_padded_sequence) and nn.GRU `encoder` /
+ * `encoder_r` (model.py:28-29, 86, 94) -- only the final hidden state is produced because the
+ * reference discards the per-step outputs (`tt`, model.py:86,94).
+ *
+ *   x4(row) = [ H2[readout[row]] | ent[seq_s[q]] | rel[seq_r[q]] | glob[row_glob[row]] ]  (4h)
+ *   x3(row) = [ H2[readout[row]] | ent[seq_s[q]] |                  glob[row_glob[row]] ]  (3h)
+ *   encoder  : GRU(4h -> h) over x4,  encoder_r : GRU(3h -> h) over x3, h0 = 0, gate order r,z,n.
+ *
+ *   Sequences are sorted by length, descending (model.py:80-81); sequence q owns rows
+ *   seq_start[q] .. seq_start[q]+seq_len[q]-1 (sequence-major).  The input projection is split
+ *   column-wise so the ent/rel/glob parts are computed once per sequence / per timestamp.
+ *
+ *   H2 [N,h]; readout [S]; row_glob [S] (row -> row of glob); glob [T,h];
+ *   ent [*,h], rel [*,h] (the direction's half, model.py:66,73); seq_s, seq_r [Q];
+ *   seq_len, seq_start [Q] (device, int32);  host_batch_sizes [max_len] (HOST: number of
+ *   sequences active at step t -- what pack_padded_sequence computes, Aggregator.py:160-165);
+ *   w_ih4 [3h,4h], w_hh4 [3h,h], b_ih4, b_hh4 [3h] : encoder;  *_3 : encoder_r ([3h,3h] ...)
+ *   hn4, hn3 [Q,h] out.   workspace: renet_gru_workspace_bytes(S, Q, T, h) bytes; its contents
+ *   after the call are what renet_gru_bwd needs (saved activations).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t renet_gru_workspace_bytes(int64_t S, int64_t Q, int64_t T, int32_t h);
+int renet_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
+                  const float* ent, const float* rel, const int32_t* seq_s, const int32_t* seq_r,
+                  const int32_t* seq_len, const int32_t* seq_start,
+                  const int32_t* host_batch_sizes, int32_t max_len,
+                  const float* w_ih4, const float* w_hh4, const float* b_ih4, const float* b_hh4,
+                  const float* w_ih3, const float* w_hh3, const float* b_ih3, const float* b_hh3,
+                  float* hn4, float* hn3,
+                  int64_t S, int64_t Q, int64_t T, int32_t h,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Materialise the packed GRU inputs exactly as the reference's aggregator returns them
+ * (PackedSequence.data, time-major: Aggregator.py:160-165):  X4 [S,4h], X3 [S,3h];
+ * packed_row [S] maps packed position -> sequence-major row. */
+int renet_pack_inputs(const float* H2, const int32_t* readout, const int32_t* row_glob,
+                      const float* glob, const float* ent, const float* rel,
+                      const int32_t* row_seq, const int32_t* seq_s, const int32_t* seq_r,
+                      const int32_t* packed_row, float* X4, float* X3,
+                      int64_t S, int32_t h, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RENET_B200_H */

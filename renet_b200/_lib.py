@@ -1,0 +1,78 @@
+"""ctypes binding of librenet_b200.so (the C-ABI declared in include/renet_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+PyTorch is used only for device memory and streams; raw device pointers cross the boundary.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'librenet_b200.so')
+
+_vp, _i32, _i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+
+# name -> (restype, argtypes); mirrors include/renet_b200.h one to one
+SIGNATURES = {
+    'renet_version': (ctypes.c_int, []),
+    'renet_last_error': (ctypes.c_char_p, []),
+    'renet_launch_count': (_i64, []),
+    'renet_csr_workspace_bytes': (_i64, [_i64, _i64]),
+    'renet_build_csr': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    'renet_rgcn_block_fwd': (ctypes.c_int, [_vp] * 9 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'renet_selfloop_gemm': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    'renet_selfloop_gemm_bwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    'renet_rgcn_gather': (ctypes.c_int, [_vp] * 8 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'renet_rgcn_block_bwd': (ctypes.c_int, [_vp] * 17 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'renet_scatter_add_rows': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
+    'renet_gru_workspace_bytes': (_i64, [_i64, _i64, _i64, _i32]),
+    'renet_gru_fwd': (ctypes.c_int, [_vp] * 11 + [_i32] + [_vp] * 10 + [_i64, _i64, _i64, _i32, _vp, _i64, _vp]),
+    'renet_pack_inputs': (ctypes.c_int, [_vp] * 12 + [_i64, _i32, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises if it has not been built (python -m renet_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                'renet_b200: %s is missing -- build it with `python -m renet_b200.build` '
+                '(there is no CPU or PyTorch fallback for the hot path)' % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)     # AttributeError if the .so does not export the symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().renet_last_error().decode('utf-8', 'replace')
+        raise RuntimeError('renet_b200: %s failed (status %d): %s' % (what, rc, msg))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('renet_b200: the hot path runs on CUDA only (got a %s tensor); '
+                               'there is no CPU fallback' % t.device)
+
+
+def launch_count():
+    return int(lib().renet_launch_count())

@@ -1,0 +1,131 @@
+"""RGCNAggregator with the reference's surface (reference Aggregator.py:109-237) on the sm_100a kernels.
+
+Kept verbatim from the reference: constructor signature and attributes, sub-modules ``rgcn1`` /
+``rgcn2`` (so state_dict keys ``aggregator.rgcn{1,2}.{weight,loop_weight}`` carry over),
+``forward`` / ``predict_batch`` returning two ``PackedSequence`` (4h and 3h wide, sequences sorted by
+history length, time-major), ``predict`` returning dense ``[len,4h]`` / ``[len,3h]`` tensors.
+
+New (used by ``RENet.forward``): ``encode`` runs history batching -> 2 fused RGCN layers -> fused
+read-out + GRU without ever materialising the padded/packed inputs.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.utils.rnn import PackedSequence
+
+from . import _lib
+from .rgcn import RGCNBlockLayer as RGCNLayer
+from .utils import assemble_history_batch, global_rows
+
+
+class _PackInputsFn(torch.autograd.Function):
+    """X4/X3 in packed (time-major) order, Aggregator.py:139-165 without the Python loop."""
+
+    @staticmethod
+    def forward(ctx, H2, ent, rel, glob, hb, seq_s, seq_r):
+        L = _lib.lib()
+        _lib.require_cuda(H2, ent, rel, glob)
+        H2, ent, rel, glob = H2.contiguous(), ent.contiguous(), rel.contiguous(), glob.contiguous()
+        h = H2.shape[1]
+        X4 = torch.empty(hb.S, 4 * h, device=H2.device)
+        X3 = torch.empty(hb.S, 3 * h, device=H2.device)
+        rc = L.renet_pack_inputs(_lib.ptr(H2), _lib.ptr(hb.readout), _lib.ptr(hb.row_glob), _lib.ptr(glob),
+                                 _lib.ptr(ent), _lib.ptr(rel), _lib.ptr(hb.row_seq), _lib.ptr(seq_s),
+                                 _lib.ptr(seq_r), _lib.ptr(hb.packed_row), _lib.ptr(X4), _lib.ptr(X3), hb.S, h,
+                                 _lib.stream())
+        _lib.check(rc, 'renet_pack_inputs')
+        ctx.hb, ctx.seq_s, ctx.seq_r = hb, seq_s, seq_r
+        ctx.shapes = (H2.shape, ent.shape, rel.shape, glob.shape)
+        return X4, X3
+
+    @staticmethod
+    def backward(ctx, dX4, dX3):
+        hb, h = ctx.hb, ctx.shapes[0][1]
+        row = hb.packed_row.long()
+        q = hb.row_seq.long()[row]
+        dev = dX4.device
+        dH2 = torch.zeros(ctx.shapes[0], device=dev).index_add_(0, hb.readout.long()[row], dX4[:, :h] + dX3[:, :h])
+        dent = torch.zeros(ctx.shapes[1], device=dev).index_add_(0, ctx.seq_s.long()[q], dX4[:, h:2 * h] + dX3[:, h:2 * h])
+        drel = torch.zeros(ctx.shapes[2], device=dev).index_add_(0, ctx.seq_r.long()[q], dX4[:, 2 * h:3 * h])
+        dglob = torch.zeros(ctx.shapes[3], device=dev).index_add_(0, hb.row_glob.long()[row], dX4[:, 3 * h:] + dX3[:, 2 * h:])
+        return dH2, dent, drel, dglob, None, None, None
+
+
+class RGCNAggregator(nn.Module):
+    def __init__(self, h_dim, dropout, num_nodes, num_rels, num_bases, model, seq_len=10):
+        super(RGCNAggregator, self).__init__()
+        self.h_dim = h_dim
+        self.dropout = nn.Dropout(dropout)
+        self.seq_len = seq_len
+        self.num_rels = num_rels
+        self.num_nodes = num_nodes
+        self.model = model
+        self.rgcn1 = RGCNLayer(self.h_dim, self.h_dim, 2 * self.num_rels, num_bases,
+                               activation=F.relu, self_loop=True, dropout=dropout)
+        self.rgcn2 = RGCNLayer(self.h_dim, self.h_dim, 2 * self.num_rels, num_bases,
+                               activation=None, self_loop=True, dropout=dropout)
+
+    # ---------------------------------------------------------------------------------------------
+    def _batch(self, s_hist, s, graph_dict, device, sort):
+        total = 0
+        for his in s_hist[0]:
+            total += len(his)
+        if total == 0:
+            # the reference returns an unbound local here (Aggregator.py:128-129,167) and crashes
+            raise ValueError('RGCNAggregator: every history in the batch is empty '
+                             '(the reference fails on this input too, Aggregator.py:128-129,167)')
+        return assemble_history_batch(s_hist[0], s_hist[1], s.detach().reshape(-1).cpu().numpy(), graph_dict,
+                                      device, sort=sort)
+
+    def aggregate(self, hb, ent_embeds, reverse):
+        """The two RGCN layers over the batched history graph (Aggregator.py:136-139); the embedding
+        lookup ndata['h'] = ent_embeds[id] (utils.py:239) is fused into layer 1."""
+        g = hb.graph
+        H1 = self.rgcn1.apply_layer(g, ent_embeds, g.node_ent, reverse)
+        return self.rgcn2.apply_layer(g, H1, None, reverse)
+
+    def _sorted_ids(self, hb, s, r, device):
+        idx = torch.from_numpy(hb.s_idx).to(device)
+        s_tem, r_tem = s.reshape(-1)[idx], r.reshape(-1)[idx]
+        Q = hb.num_seq
+        return s_tem, r_tem, s_tem[:Q].to(torch.int32).contiguous(), r_tem[:Q].to(torch.int32).contiguous()
+
+    def _packed(self, s_hist, s, r, ent_embeds, rel_embeds, graph_dict, global_emb, reverse, sort):
+        dev = ent_embeds.device
+        hb = self._batch(s_hist, s, graph_dict, dev, sort)
+        H2 = self.aggregate(hb, ent_embeds, reverse)
+        glob = global_rows(global_emb, hb.times, self.h_dim, dev)
+        _, _, seq_s, seq_r = self._sorted_ids(hb, s, r, dev)
+        X4, X3 = _PackInputsFn.apply(H2, ent_embeds, rel_embeds, glob, hb, seq_s, seq_r)
+        X4, X3 = self.dropout(X4), self.dropout(X3)                       # Aggregator.py:157-158
+        bs = torch.from_numpy(hb.batch_sizes.astype(np.int64))
+        return PackedSequence(X4, bs), PackedSequence(X3, bs), hb
+
+    def forward(self, s_hist, s, r, ent_embeds, rel_embeds, graph_dict, global_emb, reverse):
+        """Reference Aggregator.py:124-167."""
+        p4, p3, _ = self._packed(s_hist, s, r, ent_embeds, rel_embeds, graph_dict, global_emb, reverse, True)
+        return p4, p3
+
+    def predict_batch(self, s_hist, s, r, ent_embeds, rel_embeds, graph_dict, global_emb, reverse):
+        """Reference Aggregator.py:169-214 (unsorted twin)."""
+        p4, p3, _ = self._packed(s_hist, s, r, ent_embeds, rel_embeds, graph_dict, global_emb, reverse, False)
+        return p4, p3
+
+    def predict(self, s_history, s, r, ent_embeds, rel_embeds, graph_dict, global_emb, reverse):
+        """Reference Aggregator.py:218-237: one (s, r) history -> dense [len,4h], [len,3h]."""
+        p4, p3, hb = self._packed(([s_history[0]], [s_history[1]]), s.view(-1, 1), r.view(-1, 1), ent_embeds,
+                                  rel_embeds, graph_dict, global_emb, reverse, False)
+        return p4.data, p3.data          # a single sequence: packed order == time order
+
+    # ---------------------------------------------------------------------------------------------
+    def encode(self, hist, s, r, ent_embeds, rel_embeds, graph_dict, global_emb, reverse, encoder, encoder_r):
+        """history -> RGCN x2 -> fused read-out + both GRUs.  Returns (s_h [Q,h], s_q [Q,h], hb)."""
+        from .gru import fused_gru
+        dev = ent_embeds.device
+        hb = self._batch(hist, s, graph_dict, dev, True)
+        H2 = self.aggregate(hb, ent_embeds, reverse)
+        glob = global_rows(global_emb, hb.times, self.h_dim, dev)
+        _, _, seq_s, seq_r = self._sorted_ids(hb, s, r, dev)
+        s_h, s_q = fused_gru(H2, ent_embeds, rel_embeds, glob, hb, seq_s, seq_r, encoder, encoder_r)
+        return s_h, s_q, hb

@@ -1,0 +1,246 @@
+// extern "C" entry points of librenet_b200.so (declared in include/renet_b200.h).
+#include <cub/device/device_radix_sort.cuh>
+
+#include <atomic>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace renet {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// launchers defined in the other translation units
+int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
+                       const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout,
+                       int64_t N, int64_t E, int d_in, int d_out, int nb, int relu, int has_loop,
+                       cudaStream_t stream);
+int launch_rgcn_bwd(const float* H, const int32_t* h_index, const float* W, const float* Wloop,
+                    const int32_t* t_row_ptr, const int32_t* t_col_dst, const int32_t* t_col_type,
+                    const int32_t* rel_ptr, const int32_t* rel_src, const int32_t* rel_dst, const float* norm,
+                    const float* Hout, const float* dHout, float* dH, float* dW, float* dWloop, float* G_ws,
+                    int64_t N, int64_t E, int d_in, int d_out, int nb, int R2, int relu, cudaStream_t stream);
+int launch_selfloop_bwd(const float* H, const int32_t* h_index, const float* Wloop, const float* dLoop, float* dH,
+                        float* dWloop, float* WloopT_ws, int64_t N, int d_in, int d_out, cudaStream_t stream);
+int launch_scatter_add_rows(const float* src, const int32_t* index, float* dst, int64_t n_rows, int d,
+                            cudaStream_t stream);
+int64_t gru_workspace_floats(int64_t S, int64_t Q, int64_t T, int h);
+int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
+                   const float* ent, const float* rel, const int32_t* seq_s, const int32_t* seq_r,
+                   const int32_t* seq_len, const int32_t* seq_start, const int32_t* host_batch_sizes,
+                   int max_len, const float* w_ih4, const float* w_hh4, const float* b_ih4, const float* b_hh4,
+                   const float* w_ih3, const float* w_hh3, const float* b_ih3, const float* b_hh3, float* hn4,
+                   float* hn3, int64_t S, int64_t Q, int64_t T, int h, float* ws_base, cudaStream_t stream);
+int launch_pack_inputs(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
+                       const float* ent, const float* rel, const int32_t* row_seq, const int32_t* seq_s,
+                       const int32_t* seq_r, const int32_t* packed_row, float* X4, float* X3, int64_t S, int h,
+                       cudaStream_t stream);
+
+namespace {
+
+__global__ void iota_kernel(int32_t* p, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int32_t)i;
+}
+
+// sorted keys -> row_ptr (handles empty rows), and gather the payload columns through perm
+__global__ void csr_finish_kernel(const int32_t* __restrict__ keys, const int32_t* __restrict__ perm,
+                                  const int32_t* __restrict__ src, const int32_t* __restrict__ etype,
+                                  int32_t* __restrict__ row_ptr, int32_t* __restrict__ col_src,
+                                  int32_t* __restrict__ col_type, int64_t N, int64_t E) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > E) return;
+  const int64_t prev = (i == 0) ? -1 : keys[i - 1];
+  const int64_t cur = (i == E) ? N : keys[i];
+  for (int64_t k = prev + 1; k <= cur; ++k) row_ptr[k] = (int32_t)i;
+  if (i < E) {
+    const int32_t p = perm[i];
+    col_src[i] = src[p];
+    if (etype != nullptr) col_type[i] = etype[p];
+  }
+}
+
+inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
+
+int key_bits(int64_t N) {
+  int b = 1;
+  while ((int64_t(1) << b) < N && b < 31) ++b;
+  return b;
+}
+
+}  // namespace
+}  // namespace renet
+
+using namespace renet;
+
+extern "C" {
+
+int renet_version(void) { return 100; /* 0.1.0 */ }
+const char* renet_last_error(void) { return g_err; }
+int64_t renet_launch_count(void) { return g_launches.load(); }
+
+int64_t renet_csr_workspace_bytes(int64_t N, int64_t E) {
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)E, 0, key_bits(N));
+  return align256((int64_t)cub_bytes) + 3 * align256(E * 4) + 256;
+}
+
+int renet_build_csr(const int32_t* dst, const int32_t* src, const int32_t* etype, int64_t N, int64_t E,
+                    int32_t* row_ptr, int32_t* col_src, int32_t* col_type, int32_t* perm, void* workspace,
+                    int64_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RENET_CHECK_ARG(N >= 0 && E >= 0 && E < (int64_t(1) << 31) && N < (int64_t(1) << 31), "renet_build_csr: bad N/E");
+  RENET_CHECK_ARG(row_ptr != nullptr, "renet_build_csr: row_ptr is null");
+  if (E == 0) {
+    RENET_CHECK_CUDA(cudaMemsetAsync(row_ptr, 0, (N + 1) * sizeof(int32_t), stream));
+    return RENET_OK;
+  }
+  RENET_CHECK_ARG(dst && src && col_src && workspace, "renet_build_csr: null pointer");
+  RENET_CHECK_ARG(etype == nullptr || col_type != nullptr, "renet_build_csr: col_type is null");
+  RENET_CHECK_ARG(workspace_bytes >= renet_csr_workspace_bytes(N, E), "renet_build_csr: workspace too small");
+  char* ws = (char*)workspace;
+  int32_t* keys_out = (int32_t*)ws;            ws += align256(E * 4);
+  int32_t* vals_in = (int32_t*)ws;             ws += align256(E * 4);
+  int32_t* vals_out = perm ? perm : (int32_t*)ws;  ws += align256(E * 4);
+  size_t cub_bytes = (size_t)(workspace_bytes - (ws - (char*)workspace));
+  const unsigned nb = (unsigned)((E + 256) / 256);
+  iota_kernel<<<nb, 256, 0, stream>>>(vals_in, E);
+  RENET_CHECK_LAUNCH("iota_kernel");
+  RENET_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(ws, cub_bytes, dst, keys_out, vals_in, vals_out, (int)E, 0,
+                                                   key_bits(N), stream));
+  count_launch(3);
+  csr_finish_kernel<<<nb, 256, 0, stream>>>(keys_out, vals_out, src, etype, row_ptr, col_src, col_type, N, E);
+  RENET_CHECK_LAUNCH("csr_finish_kernel");
+  return RENET_OK;
+}
+
+static int check_layer_args(const char* fn, const void* H, const void* W, const void* row_ptr, const void* norm,
+                            const void* Hout, int64_t N, int64_t E, int d_in, int d_out, int nb, int R2) {
+  RENET_CHECK_ARG(N >= 0 && E >= 0 && N < (int64_t(1) << 31) && E < (int64_t(1) << 31), "%s: bad N/E", fn);
+  RENET_CHECK_ARG(d_in > 0 && d_out > 0 && nb > 0 && d_in % nb == 0 && d_out % nb == 0,
+                  "%s: d_in=%d d_out=%d must be positive multiples of num_bases=%d", fn, d_in, d_out, nb);
+  RENET_CHECK_ARG(R2 > 0, "%s: R2 must be positive", fn);
+  if (N > 0) RENET_CHECK_ARG(H && W && row_ptr && norm && Hout, "%s: null pointer", fn);
+  RENET_CHECK_ARG(E > 0 || d_in == d_out, "%s: a graph without edges needs d_in == d_out", fn);
+  return RENET_OK;
+}
+
+int renet_selfloop_gemm(const float* H, const int32_t* h_index, const float* Wloop, float* Hout, int64_t N,
+                        int32_t d_in, int32_t d_out, void* stream) {
+  RENET_CHECK_ARG(N >= 0 && d_in > 0 && d_out > 0, "renet_selfloop_gemm: bad shape");
+  if (N == 0) return RENET_OK;
+  RENET_CHECK_ARG(H && Wloop && Hout, "renet_selfloop_gemm: null pointer");
+  return sgemm_nn(H, h_index, d_in, Wloop, d_out, Hout, d_out, nullptr, N, d_out, d_in, false,
+                  (cudaStream_t)stream);
+}
+
+int renet_rgcn_gather(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
+                      const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout, int64_t N,
+                      int64_t E, int32_t d_in, int32_t d_out, int32_t num_bases, int32_t R2, int32_t relu,
+                      int32_t has_loop, void* stream) {
+  int rc = check_layer_args("renet_rgcn_gather", H, W, row_ptr, norm, Hout, N, E, d_in, d_out, num_bases, R2);
+  if (rc) return rc;
+  RENET_CHECK_ARG(E == 0 || (col_src && col_type), "renet_rgcn_gather: null edge arrays");
+  return launch_rgcn_gather(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, N, E, d_in, d_out, num_bases,
+                            relu, has_loop, (cudaStream_t)stream);
+}
+
+int renet_rgcn_block_fwd(const float* H, const int32_t* h_index, const float* W, const float* Wloop,
+                         const int32_t* row_ptr, const int32_t* col_src, const int32_t* col_type,
+                         const float* norm, float* Hout, int64_t N, int64_t E, int32_t d_in, int32_t d_out,
+                         int32_t num_bases, int32_t R2, int32_t relu, void* stream) {
+  int rc = check_layer_args("renet_rgcn_block_fwd", H, W, row_ptr, norm, Hout, N, E, d_in, d_out, num_bases, R2);
+  if (rc) return rc;
+  RENET_CHECK_ARG(E == 0 || (col_src && col_type), "renet_rgcn_block_fwd: null edge arrays");
+  if (N == 0) return RENET_OK;
+  if (Wloop != nullptr) {
+    rc = sgemm_nn(H, h_index, d_in, Wloop, d_out, Hout, d_out, nullptr, N, d_out, d_in, false, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return launch_rgcn_gather(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, N, E, d_in, d_out, num_bases,
+                            relu, Wloop != nullptr, (cudaStream_t)stream);
+}
+
+int renet_rgcn_block_bwd(const float* H, const int32_t* h_index, const float* W, const float* Wloop,
+                         const int32_t* t_row_ptr, const int32_t* t_col_dst, const int32_t* t_col_type,
+                         const int32_t* rel_ptr, const int32_t* rel_src, const int32_t* rel_dst, const float* norm,
+                         const float* Hout, const float* dHout, float* dH, float* dW, float* dWloop, float* G_ws,
+                         int64_t N, int64_t E, int32_t d_in, int32_t d_out, int32_t num_bases, int32_t R2,
+                         int32_t relu, void* stream) {
+  int rc = check_layer_args("renet_rgcn_block_bwd", H, W, t_row_ptr, norm, dHout, N, E, d_in, d_out, num_bases, R2);
+  if (rc) return rc;
+  RENET_CHECK_ARG(E > 0 || N == 0, "renet_rgcn_block_bwd: graphs without edges are not supported in backward");
+  RENET_CHECK_ARG(dH && dW && G_ws && (Wloop == nullptr || dWloop != nullptr), "renet_rgcn_block_bwd: null output");
+  RENET_CHECK_ARG(!relu || Hout != nullptr, "renet_rgcn_block_bwd: relu backward needs Hout");
+  RENET_CHECK_ARG(t_col_dst && t_col_type && rel_ptr && rel_src && rel_dst, "renet_rgcn_block_bwd: null edge arrays");
+  if (N == 0) return RENET_OK;
+  return launch_rgcn_bwd(H, h_index, W, Wloop, t_row_ptr, t_col_dst, t_col_type, rel_ptr, rel_src, rel_dst, norm,
+                         Hout, dHout, dH, dW, dWloop, G_ws, N, E, d_in, d_out, num_bases, R2, relu,
+                         (cudaStream_t)stream);
+}
+
+int renet_selfloop_gemm_bwd(const float* H, const int32_t* h_index, const float* Wloop, const float* dLoop,
+                            float* dH, float* dWloop, float* ws, int64_t N, int32_t d_in, int32_t d_out,
+                            void* stream) {
+  RENET_CHECK_ARG(N >= 0 && d_in > 0 && d_out > 0, "renet_selfloop_gemm_bwd: bad shape");
+  if (N == 0) return RENET_OK;
+  RENET_CHECK_ARG(H && Wloop && dLoop && dH && dWloop && ws, "renet_selfloop_gemm_bwd: null pointer");
+  return launch_selfloop_bwd(H, h_index, Wloop, dLoop, dH, dWloop, ws, N, d_in, d_out, (cudaStream_t)stream);
+}
+
+int renet_scatter_add_rows(const float* src, const int32_t* index, float* dst, int64_t n_rows, int32_t d,
+                           void* stream) {
+  RENET_CHECK_ARG(n_rows >= 0 && d > 0, "renet_scatter_add_rows: bad shape");
+  if (n_rows == 0) return RENET_OK;
+  RENET_CHECK_ARG(src && index && dst, "renet_scatter_add_rows: null pointer");
+  return launch_scatter_add_rows(src, index, dst, n_rows, d, (cudaStream_t)stream);
+}
+
+int64_t renet_gru_workspace_bytes(int64_t S, int64_t Q, int64_t T, int32_t h) {
+  return gru_workspace_floats(S, Q, T, h) * (int64_t)sizeof(float);
+}
+
+int renet_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
+                  const float* ent, const float* rel, const int32_t* seq_s, const int32_t* seq_r,
+                  const int32_t* seq_len, const int32_t* seq_start, const int32_t* host_batch_sizes,
+                  int32_t max_len, const float* w_ih4, const float* w_hh4, const float* b_ih4, const float* b_hh4,
+                  const float* w_ih3, const float* w_hh3, const float* b_ih3, const float* b_hh3, float* hn4,
+                  float* hn3, int64_t S, int64_t Q, int64_t T, int32_t h, void* workspace, int64_t workspace_bytes,
+                  void* stream) {
+  RENET_CHECK_ARG(S >= 0 && Q >= 0 && T >= 0 && h > 0 && max_len >= 0, "renet_gru_fwd: bad shape");
+  if (S == 0 || Q == 0) return RENET_OK;
+  RENET_CHECK_ARG(H2 && readout && row_glob && glob && ent && rel && seq_s && seq_r && seq_len && seq_start &&
+                      host_batch_sizes && w_ih4 && w_hh4 && b_ih4 && b_hh4 && w_ih3 && w_hh3 && b_ih3 && b_hh3 &&
+                      hn4 && hn3 && workspace,
+                  "renet_gru_fwd: null pointer");
+  RENET_CHECK_ARG(workspace_bytes >= renet_gru_workspace_bytes(S, Q, T, h), "renet_gru_fwd: workspace too small");
+  RENET_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "renet_gru_fwd: workspace must be 16-byte aligned");
+  return launch_gru_fwd(H2, readout, row_glob, glob, ent, rel, seq_s, seq_r, seq_len, seq_start, host_batch_sizes,
+                        max_len, w_ih4, w_hh4, b_ih4, b_hh4, w_ih3, w_hh3, b_ih3, b_hh3, hn4, hn3, S, Q, T, h,
+                        (float*)workspace, (cudaStream_t)stream);
+}
+
+int renet_pack_inputs(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
+                      const float* ent, const float* rel, const int32_t* row_seq, const int32_t* seq_s,
+                      const int32_t* seq_r, const int32_t* packed_row, float* X4, float* X3, int64_t S, int32_t h,
+                      void* stream) {
+  RENET_CHECK_ARG(S >= 0 && h > 0, "renet_pack_inputs: bad shape");
+  if (S == 0) return RENET_OK;
+  RENET_CHECK_ARG(H2 && readout && row_glob && glob && ent && rel && row_seq && seq_s && seq_r && packed_row &&
+                      X4 && X3,
+                  "renet_pack_inputs: null pointer");
+  return launch_pack_inputs(H2, readout, row_glob, glob, ent, rel, row_seq, seq_s, seq_r, packed_row, X4, X3, S, h,
+                            (cudaStream_t)stream);
+}
+
+}  // extern "C"

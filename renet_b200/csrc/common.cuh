@@ -1,0 +1,77 @@
+// Shared helpers for librenet_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/renet_b200.h"
+
+namespace renet {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define RENET_CHECK_ARG(cond, ...)                  \
+  do {                                              \
+    if (!(cond)) {                                  \
+      ::renet::set_error(__VA_ARGS__);              \
+      return RENET_ERR_INVALID_ARG;                 \
+    }                                               \
+  } while (0)
+
+#define RENET_CHECK_CUDA(expr)                                                        \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      ::renet::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+                         __FILE__, __LINE__);                                         \
+      return RENET_ERR_CUDA;                                                          \
+    }                                                                                 \
+  } while (0)
+
+#define RENET_CHECK_LAUNCH(name)                                                      \
+  do {                                                                                \
+    cudaError_t _e = cudaGetLastError();                                              \
+    if (_e != cudaSuccess) {                                                          \
+      ::renet::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));    \
+      return RENET_ERR_CUDA;                                                          \
+    }                                                                                 \
+    ::renet::count_launch();                                                          \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+// streaming 128-bit load that does not allocate in L1 (keeps L1 for the relation-weight table)
+__device__ __forceinline__ float4 ldg_f4_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// 128-bit vector reduction to global memory (sm_90+): one RED for four floats.
+__device__ __forceinline__ void red_add_f4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+// internal (non-exported) launchers shared between translation units -------------------------------
+// C[M,N] (ldc) = A[M,K] (rows optionally through a_index; lda) @ B[K,N] (ldb) [+ bias[N]] [+ C if accumulate]
+int sgemm_nn(const float* A, const int32_t* a_index, int64_t lda, const float* B, int64_t ldb, float* C,
+             int64_t ldc, const float* bias, int64_t M, int32_t N, int32_t K, bool accumulate,
+             cudaStream_t stream);
+// C[M,N] += / = A^T B with A [K,M] (rows of A optionally through a_index), B [K,N]:  C = A^T @ B
+int sgemm_tn(const float* A, const int32_t* a_index, int64_t lda, const float* B, int64_t ldb, float* C,
+             int64_t ldc, int32_t M, int32_t N, int64_t K, bool accumulate, cudaStream_t stream);
+// C[M,N] = A[M,K] @ B^T with B [N,K]
+int sgemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+             int64_t M, int32_t N, int32_t K, bool accumulate, cudaStream_t stream);
+
+}  // namespace renet

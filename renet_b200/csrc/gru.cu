@@ -1,0 +1,212 @@
+// Read-out + concat + GRU (reference Aggregator.py:139-165, model.py:86,94).
+//
+// The reference materialises zero-padded [Q,10,4h] / [Q,10,3h] inputs with a Python loop of 2Q
+// cat/repeat/index_put launches ("# Slow!!!", Aggregator.py:148-155) and hands them to cuDNN.
+// Here the concat never exists: W_ih . x is split column-wise into
+//     GI[row]  = H2[readout[row]] @ Wrow           (per read-out row, S x h  @ h x 6h)
+//     PQ[q]    = ent[s_q] @ Went + rel[r_q] @ Wrel + b_ih   (once per sequence)
+//     PT[t]    = glob[t] @ Wglob                   (once per distinct timestamp)
+// for both encoders at once (they share H2 rows, ent and glob), and every time step is one
+// recurrent GEMM + one fused gate kernel over the sequences still active at that step.
+#include "common.cuh"
+
+namespace renet {
+namespace {
+
+// dst[k, dst_off + o] = src[o, src_off + k]   for o < rows_src, k < h
+__global__ void pack_transpose_kernel(const float* __restrict__ src, int ld_src, int src_off, int rows_src,
+                                      float* __restrict__ dst, int ld_dst, int dst_off, int h) {
+  __shared__ float tile[32][33];
+  const int o0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    int o = o0 + i, k = k0 + tx;
+    tile[i][tx] = (o < rows_src && k < h) ? src[(int64_t)o * ld_src + src_off + k] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    int k = k0 + i, o = o0 + tx;
+    if (o < rows_src && k < h) dst[(int64_t)k * ld_dst + dst_off + o] = tile[tx][i];
+  }
+}
+
+__global__ void concat_bias_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                   int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i];
+  else if (i < 2 * n) out[i] = b[i - n];
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// One GRU time step for both encoders.  Thread = (sequence q < n_act, encoder, unit).
+//   gi = GI[row] + PQ[q] + PT[row_glob[row]]   (b_ih already folded into PQ)
+//   gh = GH[q] + b_hh                           (GH = h_prev @ W_hh^T, or absent at t = 0)
+__global__ void gru_gate_kernel(const float* __restrict__ GI, const float* __restrict__ PQ,
+                                const float* __restrict__ PT, const float* __restrict__ GH,
+                                const float* __restrict__ bhh /* [6h] */, const int32_t* __restrict__ row_glob,
+                                const int32_t* __restrict__ seq_start, const int32_t* __restrict__ seq_len,
+                                const float* __restrict__ Hprev /* [Q,2h] or null (t=0) */,
+                                float* __restrict__ Hnext /* [Q,2h] */, float* __restrict__ hn4,
+                                float* __restrict__ hn3, int n_act, int h, int t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_q = 2 * h;
+  if (i >= n_act * per_q) return;
+  const int q = i / per_q, c = i % per_q;
+  const int enc = c / h, u = c % h;
+  const int64_t row = (int64_t)seq_start[q] + t;
+  const int64_t g = (int64_t)row_glob[row];
+  const int base = enc * 3 * h + u;
+  const float* gi = GI + row * 6 * h + base;
+  const float* pq = PQ + (int64_t)q * 6 * h + base;
+  const float* pt = PT + g * 6 * h + base;
+  const float i_r = gi[0] + pq[0] + pt[0];
+  const float i_z = gi[h] + pq[h] + pt[h];
+  const float i_n = gi[2 * h] + pq[2 * h] + pt[2 * h];
+  float h_r = bhh[base], h_z = bhh[base + h], h_n = bhh[base + 2 * h], hp = 0.f;
+  if (Hprev != nullptr) {
+    const float* gh = GH + (int64_t)q * 6 * h + base;
+    h_r += gh[0]; h_z += gh[h]; h_n += gh[2 * h];
+    hp = Hprev[(int64_t)q * per_q + c];
+  }
+  const float r = sigmoidf_(i_r + h_r);
+  const float z = sigmoidf_(i_z + h_z);
+  const float n = tanhf(i_n + r * h_n);
+  const float hv = (1.f - z) * n + z * hp;
+  Hnext[(int64_t)q * per_q + c] = hv;
+  if (t == seq_len[q] - 1) (enc == 0 ? hn4 : hn3)[(int64_t)q * h + u] = hv;
+}
+
+// Packed (time-major) GRU inputs exactly as the reference aggregator returns them.
+__global__ void pack_inputs_kernel(const float* __restrict__ H2, const int32_t* __restrict__ readout,
+                                   const int32_t* __restrict__ row_glob, const float* __restrict__ glob,
+                                   const float* __restrict__ ent, const float* __restrict__ rel,
+                                   const int32_t* __restrict__ row_seq, const int32_t* __restrict__ seq_s,
+                                   const int32_t* __restrict__ seq_r, const int32_t* __restrict__ packed_row,
+                                   float* __restrict__ X4, float* __restrict__ X3, int64_t S, int h) {
+  const int64_t p = blockIdx.x;  // packed position
+  if (p >= S) return;
+  const int64_t row = packed_row[p];
+  const int q = row_seq[row];
+  const float* a = H2 + (int64_t)readout[row] * h;
+  const float* b = ent + (int64_t)seq_s[q] * h;
+  const float* c = rel + (int64_t)seq_r[q] * h;
+  const float* d = glob + (int64_t)row_glob[row] * h;
+  float* x4 = X4 + p * 4 * h;
+  float* x3 = X3 + p * 3 * h;
+  for (int i = threadIdx.x; i < h; i += blockDim.x) {
+    const float va = a[i], vb = b[i], vc = c[i], vd = d[i];
+    x4[i] = va; x4[h + i] = vb; x4[2 * h + i] = vc; x4[3 * h + i] = vd;
+    x3[i] = va; x3[h + i] = vb; x3[2 * h + i] = vd;
+  }
+}
+
+struct GruWs {
+  float *Brow, *Bent, *Brel, *Bglob, *Whh, *bih, *bhh, *GI, *PQ, *PT, *GH, *Hs;
+  int64_t total_floats;
+};
+
+inline int64_t align4(int64_t x) { return (x + 3) & ~int64_t(3); }
+
+GruWs carve(float* base, int64_t S, int64_t Q, int64_t T, int h, int max_len) {
+  GruWs w;
+  int64_t off = 0;
+  auto take = [&](int64_t n) { float* p = base ? base + off : nullptr; off += align4(n); return p; };
+  w.Brow = take((int64_t)h * 6 * h);
+  w.Bent = take((int64_t)h * 6 * h);
+  w.Brel = take((int64_t)h * 3 * h);
+  w.Bglob = take((int64_t)h * 6 * h);
+  w.Whh = take((int64_t)h * 6 * h);
+  w.bih = take(6 * h);
+  w.bhh = take(6 * h);
+  w.GI = take(S * 6 * h);
+  w.PQ = take(Q * 6 * h);
+  w.PT = take(T * 6 * h);
+  w.GH = take(Q * 6 * h);
+  w.Hs = take((int64_t)(max_len + 1) * Q * 2 * h);
+  w.total_floats = off;
+  return w;
+}
+
+constexpr int kMaxLenWs = 16;  // workspace is sized for sequences up to this long (reference: 10)
+
+}  // namespace
+
+int64_t gru_workspace_floats(int64_t S, int64_t Q, int64_t T, int h) {
+  return carve(nullptr, S, Q, T, h, kMaxLenWs).total_floats;
+}
+
+int launch_pack_inputs(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
+                       const float* ent, const float* rel, const int32_t* row_seq, const int32_t* seq_s,
+                       const int32_t* seq_r, const int32_t* packed_row, float* X4, float* X3, int64_t S, int h,
+                       cudaStream_t stream) {
+  if (S == 0) return RENET_OK;
+  pack_inputs_kernel<<<(unsigned)S, 64, 0, stream>>>(H2, readout, row_glob, glob, ent, rel, row_seq, seq_s,
+                                                     seq_r, packed_row, X4, X3, S, h);
+  RENET_CHECK_LAUNCH("pack_inputs_kernel");
+  return RENET_OK;
+}
+
+int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
+                   const float* ent, const float* rel, const int32_t* seq_s, const int32_t* seq_r,
+                   const int32_t* seq_len, const int32_t* seq_start, const int32_t* host_batch_sizes,
+                   int max_len, const float* w_ih4, const float* w_hh4, const float* b_ih4, const float* b_hh4,
+                   const float* w_ih3, const float* w_hh3, const float* b_ih3, const float* b_hh3, float* hn4,
+                   float* hn3, int64_t S, int64_t Q, int64_t T, int h, float* ws_base, cudaStream_t stream) {
+  if (max_len > kMaxLenWs) {
+    set_error("renet_gru_fwd: max_len %d exceeds the supported %d", max_len, kMaxLenWs);
+    return RENET_ERR_INVALID_ARG;
+  }
+  GruWs w = carve(ws_base, S, Q, T, h, kMaxLenWs);
+  const dim3 tb(32, 8);
+  auto pack = [&](const float* src, int ld_src, int src_off, float* dst, int ld_dst, int dst_off) -> int {
+    dim3 grid((3 * h + 31) / 32, (h + 31) / 32);
+    pack_transpose_kernel<<<grid, tb, 0, stream>>>(src, ld_src, src_off, 3 * h, dst, ld_dst, dst_off, h);
+    RENET_CHECK_LAUNCH("pack_transpose_kernel");
+    return RENET_OK;
+  };
+  int rc;
+  // column blocks of W_ih: encoder x4 = [row | ent | rel | glob], encoder_r x3 = [row | ent | glob]
+  if ((rc = pack(w_ih4, 4 * h, 0, w.Brow, 6 * h, 0))) return rc;
+  if ((rc = pack(w_ih3, 3 * h, 0, w.Brow, 6 * h, 3 * h))) return rc;
+  if ((rc = pack(w_ih4, 4 * h, h, w.Bent, 6 * h, 0))) return rc;
+  if ((rc = pack(w_ih3, 3 * h, h, w.Bent, 6 * h, 3 * h))) return rc;
+  if ((rc = pack(w_ih4, 4 * h, 2 * h, w.Brel, 3 * h, 0))) return rc;
+  if ((rc = pack(w_ih4, 4 * h, 3 * h, w.Bglob, 6 * h, 0))) return rc;
+  if ((rc = pack(w_ih3, 3 * h, 2 * h, w.Bglob, 6 * h, 3 * h))) return rc;
+  if ((rc = pack(w_hh4, h, 0, w.Whh, 6 * h, 0))) return rc;
+  if ((rc = pack(w_hh3, h, 0, w.Whh, 6 * h, 3 * h))) return rc;
+  concat_bias_kernel<<<(6 * h + 255) / 256, 256, 0, stream>>>(b_ih4, b_ih3, w.bih, 3 * h);
+  RENET_CHECK_LAUNCH("concat_bias_kernel");
+  concat_bias_kernel<<<(6 * h + 255) / 256, 256, 0, stream>>>(b_hh4, b_hh3, w.bhh, 3 * h);
+  RENET_CHECK_LAUNCH("concat_bias_kernel");
+
+  // input projections
+  if ((rc = sgemm_nn(H2, readout, h, w.Brow, 6 * h, w.GI, 6 * h, nullptr, S, 6 * h, h, false, stream))) return rc;
+  if ((rc = sgemm_nn(ent, seq_s, h, w.Bent, 6 * h, w.PQ, 6 * h, w.bih, Q, 6 * h, h, false, stream))) return rc;
+  if ((rc = sgemm_nn(rel, seq_r, h, w.Brel, 3 * h, w.PQ, 6 * h, nullptr, Q, 3 * h, h, true, stream))) return rc;
+  if ((rc = sgemm_nn(glob, nullptr, h, w.Bglob, 6 * h, w.PT, 6 * h, nullptr, T, 6 * h, h, false, stream))) return rc;
+
+  // recurrence over the packed time steps
+  const int64_t hs_stride = Q * 2 * h;
+  for (int t = 0; t < max_len; ++t) {
+    const int n_act = host_batch_sizes[t];
+    if (n_act <= 0) break;
+    const float* Hprev = (t == 0) ? nullptr : w.Hs + (int64_t)t * hs_stride;
+    float* Hnext = w.Hs + (int64_t)(t + 1) * hs_stride;
+    if (t > 0) {
+      if ((rc = sgemm_nn(Hprev, nullptr, 2 * h, w.Whh, 6 * h, w.GH, 6 * h, nullptr, n_act, 3 * h, h, false, stream)))
+        return rc;
+      if ((rc = sgemm_nn(Hprev + h, nullptr, 2 * h, w.Whh + 3 * h, 6 * h, w.GH + 3 * h, 6 * h, nullptr, n_act,
+                         3 * h, h, false, stream)))
+        return rc;
+    }
+    const int total = n_act * 2 * h;
+    gru_gate_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w.GI, w.PQ, w.PT, w.GH, w.bhh, row_glob, seq_start,
+                                                            seq_len, Hprev, Hnext, hn4, hn3, n_act, h, t);
+    RENET_CHECK_LAUNCH("gru_gate_kernel");
+  }
+  return RENET_OK;
+}
+
+}  // namespace renet
