@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- edge-messages/s of the RGCN aggregate on ICEWS18-shaped history graphs (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels through the C-ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A "step" is one training step's worth of the hot path over one batch of 1024 synthetic quadruples:
+both directions (train.py:136-137) x both RGCN layers (Aggregator.py:136-137) over the batched history
+graphs, i.e. 4 fused-layer passes = 2*(E_subj + E_obj) edge-messages.
+
+  value       device-timed: graphs already resident in HBM, K steps between CUDA events, max over ranks
+  e2e         the same work through the public API (RGCNAggregator / RENet.encode) from HOST inputs
+              (history lists, graph_dict, triplets): host batching + pinned H2D + kernels + D2H of the
+              GRU outputs, wall clock
+  roofline    the fused gather kernel alone, CUDA events around every launch in a second timed region
+  cpu_baseline  the reference's own op sequence (index_select -> bmm -> index_add, RGCN.py:79-94) on the
+              host cores, bounded sample
+
+L2 hygiene: the timed steps rotate over a pool of distinct pre-built batches whose combined footprint
+(graph arrays + layer outputs) exceeds 2x the 126 MB L2 ("l2": "rotating-pool" in config).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H_DIM, NUM_BASES, BATCH = 200, 100, 1024
+METRIC = 'rgcn_aggregate_edge_messages_per_sec'
+UNIT = 'edge-msg/s'
+WORKLOAD = 'ICEWS18-shaped synthetic TKG (23033 ent, 256 rel, 240 timestamps), n_hidden=200 num_bases=100 batch=1024'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--timestamps', type=int, default=240)
+    ap.add_argument('--pool', type=int, default=8, help='distinct pre-built batches the timed steps rotate over')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def algorithmic_bytes(N, E, R2):
+    """SURVEY.md section 8(d), fp32 features, int32 indices, per fused-gather launch:
+    E*(4h + 12) + N*(4h loop read + 4h write + 4 norm) + R2*(h*h/nb)*4."""
+    return E * (4 * H_DIM + 12) + N * (8 * H_DIM + 4) + R2 * (H_DIM * H_DIM // NUM_BASES) * 4
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get('rgcn_gather_d200_bytes_per_launch')
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(tkg, torch, steps, warmup):
+    """The reference's CPU path for the aggregate: its own op sequence per layer (RGCN.py:79-94:
+    index_select of the [E,400] weights, bmm over E*100 1x2.2x2 products, index_add reduce, norm, self-loop
+    mm, relu) restated in oracle/restate.py, on all host cores.  One step = ONE direction x 2 layers of one
+    batch (a bounded sample of the GPU arm's step, which is two directions)."""
+    from oracle import restate
+    from renet_b200 import utils
+    torch.set_num_threads(os.cpu_count() or 1)
+    q, sh, oh = tkg.batch(0, BATCH, tail_only=False)
+    hb = utils.assemble_history_batch_host(sh[0], sh[1], q[:, 0], tkg.graph_dict)
+    g = hb.graph
+    N, E = len(g['node_ent']), len(g['col_src'])
+    gen = torch.Generator().manual_seed(0)
+    ent = torch.randn(tkg.num_e, H_DIM, generator=gen) * 0.1
+    W = [torch.randn(2 * tkg.num_r, 4 * NUM_BASES, generator=gen) * 0.1 for _ in range(2)]
+    Wl = [torch.randn(H_DIM, H_DIM, generator=gen) * 0.07 for _ in range(2)]
+    src = torch.from_numpy(g['col_src'].astype(np.int64))
+    dst = torch.from_numpy(np.repeat(np.arange(N), np.diff(g['row_ptr'])))
+    et = torch.from_numpy(g['col_type_s'].astype(np.int64))
+    norm = torch.from_numpy(g['norm'])
+    ids = torch.from_numpy(g['node_ent'])
+
+    def step():
+        H0 = ent[ids]
+        H1 = restate.rgcn_block_layer_ref_ops(H0, W[0], Wl[0], src, dst, et, norm, True, NUM_BASES)
+        return restate.rgcn_block_layer_ref_ops(H1, W[1], Wl[1], src, dst, et, norm, False, NUM_BASES)
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            step()
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            step()
+            times.append(time.perf_counter() - t0)
+    med = float(np.median(times))
+    return {'value': 2 * E / med, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': 'one direction x 2 layers of one batch (N=%d, E=%d), reference op sequence '
+                      '(index_select+bmm+index_add) in torch CPU fp32, median of %d' % (N, E, steps),
+            'ms_per_step': med * 1e3, 'edge_msgs_per_step': 2 * E}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    from renet_b200 import synthetic
+    tkg = synthetic.SyntheticTKG('icews18', seed=999, num_timestamps=args.timestamps, h_dim=H_DIM)
+    steps = max(1, min(args.steps, 5))
+    res = cpu_reference_sample(tkg, torch, steps, max(1, min(args.warmup, 1)))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': res['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': steps, 'warmup': 1, 'ms_per_step': res['ms_per_step'], 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'sample': res['sample']},
+            'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+            'e2e': {'value': res['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from renet_b200 import _lib, synthetic, utils
+    from renet_b200.model import RENet
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the hot path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    L = _lib.lib()
+
+    # ---- workload: every rank owns its own shard of the stream (weak scaling, no data-path collective)
+    tkg = synthetic.SyntheticTKG('icews18', seed=999 + rank, num_timestamps=args.timestamps, h_dim=H_DIM)
+    torch.manual_seed(999)
+    model = RENet(tkg.num_e, H_DIM, tkg.num_r, dropout=0).to(dev).eval()
+    model.global_emb = {t: v.to(dev) for t, v in tkg.global_emb.items()}
+    agg = model.aggregator
+    ent = model.ent_embeds.detach()
+    R2 = 2 * tkg.num_r
+
+    pool = []
+    for i in range(args.pool):
+        q, sh, oh = tkg.batch(i, BATCH, tail_only=False)
+        entry = {'q': q, 'sh': sh, 'oh': oh, 'dirs': []}
+        for hist, col, reverse in ((sh, 0, False), (oh, 2, True)):
+            hb = utils.assemble_history_batch(hist[0], hist[1], q[:, col], tkg.graph_dict, dev)
+            g = hb.graph
+            entry['dirs'].append({'hb': hb, 'g': g, 'reverse': reverse, 'ct': g.col_type(reverse),
+                                  'H1': torch.empty(g.N, H_DIM, device=dev), 'H2': torch.empty(g.N, H_DIM, device=dev)})
+        pool.append(entry)
+    msgs_per_step = [sum(2 * d['g'].E for d in e['dirs']) for e in pool]
+    pool_bytes = sum(sum(d['g'].E * 12 + d['g'].N * (8 + 1600) for d in e['dirs']) for e in pool)
+    W1, L1, W2, L2 = (agg.rgcn1.weight.detach(), agg.rgcn1.loop_weight.detach(), agg.rgcn2.weight.detach(),
+                      agg.rgcn2.loop_weight.detach())
+    P = _lib.ptr
+    stream = _lib.stream()
+
+    def layer(d, H, h_index, W, Wl, out, relu, ev=None):
+        g = d['g']
+        _lib.check(L.renet_selfloop_gemm(P(H), P(h_index), P(Wl), P(out), g.N, H_DIM, H_DIM, stream), 'gemm')
+        if ev is not None:
+            ev[0].record()
+        _lib.check(L.renet_rgcn_gather(P(H), P(h_index), P(W), P(g.row_ptr), P(g.col_src), P(d['ct']), P(g.norm),
+                                       P(out), g.N, g.E, H_DIM, H_DIM, NUM_BASES, R2, int(relu), 1, stream), 'gather')
+        if ev is not None:
+            ev[1].record()
+
+    def device_step(e, events=None):
+        k = 0
+        for d in e['dirs']:
+            layer(d, ent, d['g'].node_ent, W1, L1, d['H1'], True, events[k] if events else None)
+            layer(d, d['H1'], None, W2, L2, d['H2'], False, events[k + 1] if events else None)
+            k += 2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- region A: `value` ----------------------------------------------------------------------------
+    for i in range(args.warmup):
+        device_step(pool[i % len(pool)])
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    n0 = _lib.launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    total_msgs = 0
+    for i in range(args.steps):
+        device_step(pool[(args.warmup + i) % len(pool)])
+        total_msgs += msgs_per_step[(args.warmup + i) % len(pool)]
+    end.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    elapsed_ms = start.elapsed_time(end)
+    clk = clocks.stop()
+    t = torch.tensor([elapsed_ms, float(total_msgs)], device=dev, dtype=torch.float64)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        elapsed_ms, total_msgs = tmax[0].item(), tsum[1].item()
+    value = total_msgs / (elapsed_ms * 1e-3)
+
+    # ---- region B: per-launch time of the fused gather kernel (roofline) ---------------------------------
+    ev_steps = []
+    for i in range(args.steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(4)]
+        device_step(pool[(args.warmup + i) % len(pool)], evs)
+        ev_steps.append((pool[(args.warmup + i) % len(pool)], evs))
+    torch.cuda.synchronize()
+    g_ms, g_bytes = [], []
+    for e, evs in ev_steps:
+        for k, (a, b) in enumerate(evs):
+            d = e['dirs'][k // 2]
+            g_ms.append(a.elapsed_time(b))
+            g_bytes.append(algorithmic_bytes(d['g'].N, d['g'].E, R2))
+    peak, peak_src = measured_peak_gbs()
+    achieved = float(np.sum(g_bytes) / (np.sum(g_ms) * 1e-3) / 1e9)
+    roofline = {'kernel': 'rgcn_gather_d200_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': ncu_traffic(), 'peak_source': peak_src,
+                'avg_launch_us': float(np.mean(g_ms) * 1e3), 'algorithmic_bytes_per_launch': float(np.mean(g_bytes)),
+                'note': 'features are L2-resident at this size (25 MB); DRAM traffic is below the algorithmic bytes'}
+
+    # ---- GRU (reported separately) -------------------------------------------------------------------------
+    from renet_b200.gru import fused_gru
+    gru_ms = None
+    try:
+        with torch.no_grad():
+            e = pool[0]
+            rel = model.rel_embeds[:tkg.num_r]
+            d = e['dirs'][0]
+            hb = d['hb']
+            seq = agg._sorted_ids(hb, torch.from_numpy(e['q'][:, 0]).to(dev), torch.from_numpy(e['q'][:, 1]).to(dev), dev)
+            glob = utils.global_rows(model.global_emb, hb.times, H_DIM, dev)
+            for _ in range(2):
+                fused_gru(d['H2'], ent, rel, glob, hb, seq[2], seq[3], model.encoder, model.encoder_r)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                fused_gru(d['H2'], ent, rel, glob, hb, seq[2], seq[3], model.encoder, model.encoder_r)
+            b.record(); torch.cuda.synchronize()
+            gru_ms = a.elapsed_time(b) / 5
+    except Exception as ex:   # the aggregate metric does not depend on it
+        gru_ms = 'failed: %s' % ex
+
+    # ---- e2e: public API from host inputs ----------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def api_step(e):
+            batch = torch.from_numpy(e['q']).pin_memory().to(dev, non_blocking=True)
+            outs, h2d, msgs = [], batch.numel() * 8, 0
+            with torch.no_grad():
+                for subj in (True, False):
+                    s, r, o, s_h, s_q, _ = model.encode(batch, e['sh'], e['oh'], tkg.graph_dict, subject=subj)
+                    outs.append(torch.cat((s_h, s_q), 1))
+            res = torch.cat(outs).cpu()        # D2H of the GRU outputs
+            return h2d, res.numel() * 4
+
+        for i in range(max(1, min(args.warmup, 2))):
+            api_step(pool[i % len(pool)])
+        barrier()
+        k_e2e = max(2, min(args.steps, 6))
+        t0 = time.perf_counter()
+        h2d = d2h = 0
+        msgs = 0
+        for i in range(k_e2e):
+            e = pool[(args.warmup + i) % len(pool)]
+            a, b = api_step(e)
+            h2d += a + sum(d['hb'].h2d_bytes for d in e['dirs']); d2h += b
+            msgs += msgs_per_step[(args.warmup + i) % len(pool)]
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt, float(msgs)], device=dev, dtype=torch.float64)
+        if world > 1:
+            a = tt.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+            b = tt.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            dt, msgs = a[0].item(), b[1].item()
+        e2e = {'value': msgs / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d / k_e2e), 'd2h_bytes_per_step': int(d2h / k_e2e),
+               'ms_per_step': dt / k_e2e * 1e3, 'steps': k_e2e,
+               'what': 'RENet.encode x2 directions from host history lists: numpy batching + pinned H2D + RGCN x2 + '
+                       'fused read-out/GRU + D2H of [Q,2h] outputs'}
+
+    cpu = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_sample(tkg, torch, 3, 1)
+        cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+
+    if rank == 0:
+        g0 = pool[0]['dirs']
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': WORKLOAD, 'step': '2 directions x 2 RGCN layers (self-loop GEMM + fused gather)',
+                           'nodes_per_direction': [d['g'].N for d in g0], 'edges_per_direction': [d['g'].E for d in g0],
+                           'edge_msgs_per_step': msgs_per_step[0], 'l2': 'rotating-pool', 'pool_batches': len(pool),
+                           'pool_bytes': int(pool_bytes), 'parallelism': 'dp%d (independent shards, no data-path collective)' % world},
+                'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
+                'gru_ms_one_direction': gru_ms}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

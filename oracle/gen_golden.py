@@ -1,0 +1,297 @@
+"""TEST INFRASTRUCTURE ONLY -- writes tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the authoring container only (needs /root/reference):
+
+    python oracle/gen_golden.py
+
+Every vector below is produced by the reference's own classes (RGCN.RGCNBlockLayer, utils.*,
+Aggregator.RGCNAggregator, model.RENet) imported through oracle/ref_loader.py over the pure-torch DGL
+stand-in, on CPU fp32, dropout 0.  The fixtures are small and committed; the GPU box (which has no
+/root/reference) checks both oracle/restate.py and the CUDA path against them.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+def det_params(shapes, seed):
+    """Deterministic parameter values, reproducible without the reference: for each name in sorted
+    order, uniform(-a, a) with a = sqrt(6/(fan_in+fan_out)) * sqrt(2) (xavier/relu-gain-like);
+    1-D tensors uniform(-0.05, 0.05)."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for name in sorted(shapes):
+        shp = tuple(shapes[name])
+        if len(shp) == 1:
+            out[name] = (torch.rand(shp, generator=g) - 0.5) * 0.1
+        else:
+            a = (6.0 / (shp[0] + shp[1])) ** 0.5 * 2 ** 0.5
+            out[name] = (torch.rand(shp, generator=g) * 2 - 1) * a
+    return out
+
+
+def shim_graph(ns, n, src, dst, type_s, type_o, norm=None):
+    g = ns.dgl.DGLGraph()
+    g.add_nodes(n)
+    g.add_edges(src, dst)
+    if norm is None:
+        norm = ns.utils.comp_deg_norm(g)
+    g.ndata['norm'] = torch.as_tensor(norm, dtype=torch.float32).view(-1, 1)
+    g.edata['type_s'] = torch.as_tensor(type_s, dtype=torch.long)
+    g.edata['type_o'] = torch.as_tensor(type_o, dtype=torch.long)
+    return g
+
+
+def run_layer(ns, case):
+    """Reference RGCNBlockLayer forward + backward on one case dict (numpy inputs)."""
+    import torch.nn.functional as F
+    d_in, d_out, nb, R2 = case['d_in'], case['d_out'], case['nb'], case['R2']
+    layer = ns.RGCN.RGCNBlockLayer(d_in, d_out, R2, nb, activation=F.relu if case['relu'] else None,
+                                   self_loop=case['self_loop'], dropout=0.0)
+    with torch.no_grad():
+        layer.weight.copy_(torch.from_numpy(case['W']))
+        if case['self_loop']:
+            layer.loop_weight.copy_(torch.from_numpy(case['Wloop']))
+    g = shim_graph(ns, case['N'], case['src'], case['dst'], case['type_s'], case['type_o'], case.get('norm'))
+    H = torch.from_numpy(case['H']).clone().requires_grad_(True)
+    g.ndata['h'] = H
+    layer(g, bool(case['reverse']))
+    out = g.ndata['h']
+    res = {'out': out.detach().numpy().copy(), 'norm': g.ndata['norm'].view(-1).numpy().copy()}
+    if case['N'] > 0:
+        G = torch.from_numpy(case['G'])
+        (out * G).sum().backward()
+        res['dH'] = H.grad.numpy().copy()
+        res['dW'] = layer.weight.grad.numpy().copy()
+        if case['self_loop']:
+            res['dWloop'] = layer.loop_weight.grad.numpy().copy()
+    return res
+
+
+def layer_cases():
+    rng = np.random.RandomState(1234)
+    cases = []
+
+    def mk(name, N, src, dst, ts, to, d, nb, R2, relu, reverse, self_loop=True, int_w=False, norm=None):
+        si = d // nb
+        if int_w:
+            W = rng.randint(-2, 3, size=(R2, nb * si * si)).astype(np.float32)
+            Wl = rng.randint(-1, 2, size=(d, d)).astype(np.float32)
+            H = rng.randint(-3, 4, size=(N, d)).astype(np.float32)
+        else:
+            W = (rng.rand(R2, nb * si * si).astype(np.float32) * 2 - 1) * 0.3
+            Wl = (rng.rand(d, d).astype(np.float32) * 2 - 1) * 0.2
+            H = rng.randn(N, d).astype(np.float32)
+        c = dict(name=name, N=N, src=np.asarray(src, np.int64), dst=np.asarray(dst, np.int64),
+                 type_s=np.asarray(ts, np.int64), type_o=np.asarray(to, np.int64), d_in=d, d_out=d, nb=nb, R2=R2,
+                 relu=int(relu), reverse=int(reverse), self_loop=bool(self_loop), W=W, Wloop=Wl, H=H,
+                 G=rng.randn(N, d).astype(np.float32))
+        if norm is not None:
+            c['norm'] = np.asarray(norm, np.float32)
+        cases.append(c)
+
+    R = 2
+    # (1) hand KAT: triples {(0,r0,1),(2,r1,1)} -> get_big_graph edge layout [s->o.., o->s..]
+    mk('hand_kat', 3, [0, 2, 1, 1], [1, 1, 0, 2], [0, 1, 0 + R, 1 + R], [0 + R, 1 + R, 0, 1], 4, 2, 2 * R, False, False, int_w=True)
+    # (2) duplicate edge: same triple twice -> in-degree 2, message counted twice
+    mk('dup_edge', 2, [0, 0, 1, 1], [1, 1, 0, 0], [0, 0, R, R], [R, R, 0, 0], 4, 2, 2 * R, False, False, int_w=True)
+    # (3) reverse selects type_o
+    mk('reverse', 3, [0, 2, 1, 1], [1, 1, 0, 2], [0, 1, 0 + R, 1 + R], [0 + R, 1 + R, 0, 1], 4, 2, 2 * R, True, True, int_w=True)
+    # (4) explicit norm different from 1/in-degree (sub-graph norm is whatever the caller recomputed)
+    mk('custom_norm', 3, [0, 2, 1], [1, 1, 0], [0, 1, 2], [2, 3, 0], 4, 2, 4, True, False, norm=[0.5, 0.25, 1.0])
+    # (5) isolated nodes (no in-edge) + relu + no self loop
+    mk('isolated_noloop', 5, [0, 1], [1, 0], [0, 1], [1, 0], 8, 4, 2, True, False, self_loop=False)
+    # (6) random differential, RE-Net's real shape d=200 nb=100
+    for N, E, R2, relu, rev in ((1, 3, 8, True, False), (33, 200, 16, True, True), (300, 2500, 32, False, False),
+                                (257, 4000, 256, True, True)):
+        src = rng.randint(0, N, E); dst = rng.randint(0, N, E)
+        if N == 257:   # heavy-degree node (in-degree > 128) and empty relations
+            dst[:300] = 7
+        ts = rng.randint(0, R2, E); to = rng.randint(0, R2, E)
+        mk('rand_N%d_E%d' % (N, E), N, src, dst, ts, to, 200, 100, R2, relu, rev)
+    # (7) small generic shape with si=so=3
+    src = rng.randint(0, 20, 90); dst = rng.randint(0, 20, 90)
+    mk('generic_d12_nb4', 20, src, dst, rng.randint(0, 6, 90), rng.randint(0, 6, 90), 12, 4, 6, True, False)
+    return cases
+
+
+def gen_layers(ns):
+    blob = {}
+    names = []
+    with ref_loader.cpu_patches():
+        for c in layer_cases():
+            res = run_layer(ns, c)
+            names.append(c['name'])
+            for k, v in c.items():
+                if k != 'name':
+                    blob['%s/%s' % (c['name'], k)] = np.asarray(v)
+            for k, v in res.items():
+                blob['%s/ref_%s' % (c['name'], k)] = v
+        # (8) zero-edge graph: DGL 0.4 skips the reduce, only apply (h*norm) runs
+        g = shim_graph(ns, 4, [], [], [], [])
+        import torch.nn.functional as F
+        layer = ns.RGCN.RGCNBlockLayer(4, 4, 2, 2, activation=F.relu, self_loop=True, dropout=0.0)
+        H = torch.arange(16, dtype=torch.float32).view(4, 4) - 6
+        g.ndata['h'] = H.clone()
+        layer(g, False)
+        blob['zero_edge/H'] = H.numpy(); blob['zero_edge/W'] = layer.weight.detach().numpy()
+        blob['zero_edge/Wloop'] = layer.loop_weight.detach().numpy()
+        blob['zero_edge/ref_out'] = g.ndata['h'].detach().numpy()
+    blob['names'] = np.asarray(names)
+    np.savez_compressed(os.path.join(OUT, 'layer_cases.npz'), **blob)
+    print('layer_cases.npz: %d cases' % len(names))
+
+
+RENET_SHAPES = lambda num_e, h, R, nb: {  # noqa: E731
+    'rel_embeds': (2 * R, h), 'ent_embeds': (num_e, h),
+    'encoder.weight_ih_l0': (3 * h, 4 * h), 'encoder.weight_hh_l0': (3 * h, h),
+    'encoder.bias_ih_l0': (3 * h,), 'encoder.bias_hh_l0': (3 * h,),
+    'encoder_r.weight_ih_l0': (3 * h, 3 * h), 'encoder_r.weight_hh_l0': (3 * h, h),
+    'encoder_r.bias_ih_l0': (3 * h,), 'encoder_r.bias_hh_l0': (3 * h,),
+    'aggregator.rgcn1.weight': (2 * R, nb * (h // nb) ** 2), 'aggregator.rgcn1.loop_weight': (h, h),
+    'aggregator.rgcn2.weight': (2 * R, nb * (h // nb) ** 2), 'aggregator.rgcn2.loop_weight': (h, h),
+    'linear.weight': (num_e, 3 * h), 'linear.bias': (num_e,),
+    'linear_r.weight': (R, 2 * h), 'linear_r.bias': (R,),
+}
+
+
+def det_global_emb(times, h, seed):
+    g = torch.Generator().manual_seed(seed)
+    return {int(t): 0.1 * torch.randn(1, 1, h, generator=g) for t in sorted(int(x) for x in times)}
+
+
+def run_renet(ns, quads, num_e, R, h, nb, sel, seed, hist_builder):
+    """Reference RENet.forward for both directions on the samples ``sel`` of ``quads``."""
+    with ref_loader.cpu_patches():
+        gd = {}
+        for t in np.unique(quads[:, 3]):
+            gd[int(t)] = ns.utils.get_big_graph(quads[quads[:, 3] == t][:, :3], R)
+        S, ST, O, OT = hist_builder(quads)
+        m = ns.model.RENet(num_e, h, R, dropout=0, model=0, seq_len=10, num_k=10)
+        if nb != 100:
+            m.aggregator = ns.Aggregator.RGCNAggregator(h, 0, num_e, R, nb, 0, 10)
+        params = det_params(RENET_SHAPES(num_e, h, R, nb), seed)
+        m.load_state_dict(params, strict=True)
+        m.global_emb = det_global_emb(np.unique(quads[:, 3]), h, seed + 1)
+        batch = torch.from_numpy(quads[sel]).long()
+        sh = ([S[i] for i in sel], [ST[i] for i in sel])
+        oh = ([O[i] for i in sel], [OT[i] for i in sel])
+        res = {}
+        captured = {}
+        orig_enc, orig_encr = m.encoder.forward, m.encoder_r.forward
+
+        def cap(name, orig):
+            def f(x, *a, **k):
+                captured[name] = x
+                return orig(x, *a, **k)
+            return f
+        m.encoder.forward = cap('p4', orig_enc)
+        m.encoder_r.forward = cap('p3', orig_encr)
+        for subj in (True, False):
+            m.zero_grad()
+            loss = m(batch, sh, oh, gd, subject=subj)
+            loss.backward()
+            tag = 'subj' if subj else 'obj'
+            res[tag + '/loss'] = np.float64(loss.item())
+            res[tag + '/x4_sum'] = captured['p4'].data.detach().double().sum(0).numpy()     # column sums of the packed inputs
+            res[tag + '/x3_sum'] = captured['p3'].data.detach().double().sum(0).numpy()
+            res[tag + '/x4_head'] = captured['p4'].data[:16].detach().numpy().copy()
+            res[tag + '/batch_sizes'] = captured['p4'].batch_sizes.numpy().copy()
+            with torch.no_grad():
+                _, s_h = orig_enc(captured['p4'])
+                _, s_q = orig_encr(captured['p3'])
+            res[tag + '/s_h'] = s_h.view(-1, h).numpy().copy()
+            res[tag + '/s_q'] = s_q.view(-1, h).numpy().copy()
+            for k, p in m.named_parameters():
+                if p.numel() > 20000 and p.dim() == 2:
+                    # large: store the norm and the two 1-D marginals instead of the full gradient
+                    res['%s/grad_norm/%s' % (tag, k)] = np.float64(p.grad.double().norm().item())
+                    res['%s/grad_rowsum/%s' % (tag, k)] = p.grad.double().sum(1).numpy()
+                    res['%s/grad_colsum/%s' % (tag, k)] = p.grad.double().sum(0).numpy()
+                else:
+                    res['%s/grad/%s' % (tag, k)] = p.grad.numpy().copy()
+    return res
+
+
+def gen_renet_tiny(ns):
+    sys.path.insert(0, ROOT)
+    from oracle import restate
+    rng = np.random.RandomState(7)
+    num_e, R, T, h, nb = 50, 6, 14, 8, 4
+    quads = []
+    for t in range(T):
+        n = rng.randint(20, 40)
+        s = rng.zipf(1.4, n) % num_e
+        o = rng.randint(0, num_e, n)
+        r = rng.randint(0, R, n)
+        quads += [[a, b, c, t * 24] for a, b, c in zip(s, r, o)]
+    quads = np.asarray(quads, dtype=np.int64)
+    sel = np.arange(len(quads) - 48, len(quads))
+    res = run_renet(ns, quads, num_e, R, h, nb, sel, 11, lambda q: restate.build_history(q, num_e))
+    res.update(quads=quads.astype(np.int32), sel=sel, num_e=num_e, R=R, h=h, nb=nb, seed=11)
+    np.savez_compressed(os.path.join(OUT, 'renet_tiny.npz'), **res)
+    print('renet_tiny.npz: loss', res['subj/loss'], res['obj/loss'])
+
+
+def gen_renet_icews18_slice(ns):
+    """A real ICEWS18 slice: the first 13 timestamps of the reference's train.txt, batch = 192 samples
+    of the last two of them, h=200 / num_bases=100 (the real model shape)."""
+    from oracle import restate
+    q = np.loadtxt(os.path.join(ref_loader.REFERENCE_DIR, 'data', 'ICEWS18', 'train.txt'), dtype=np.int64)[:, :4]
+    ts = np.unique(q[:, 3])[:13]
+    quads = q[q[:, 3] <= ts[-1]]
+    num_e, R, h, nb = 23033, 256, 200, 100
+    cand = np.flatnonzero(quads[:, 3] >= ts[-2])
+    sel = np.random.RandomState(999).permutation(cand)[:192]
+    res = run_renet(ns, quads, num_e, R, h, nb, sel, 5, lambda qq: restate.build_history(qq, num_e))
+    res.update(quads=quads.astype(np.int32), sel=sel, num_e=num_e, R=R, h=h, nb=nb, seed=5)
+    np.savez_compressed(os.path.join(OUT, 'renet_icews18_slice.npz'), **res)
+    print('renet_icews18_slice.npz: loss', res['subj/loss'], res['obj/loss'], 'quads', len(quads))
+
+
+def gen_graph_kats(ns):
+    """utils.get_big_graph / make_subgraph / get_sorted_s_r_embed_rgcn structure on a tiny stream."""
+    from oracle import restate
+    rng = np.random.RandomState(3)
+    num_e, R = 12, 3
+    quads = np.asarray([[rng.randint(num_e), rng.randint(R), rng.randint(num_e), t * 24]
+                        for t in range(6) for _ in range(9)], dtype=np.int64)
+    blob = {'quads': quads.astype(np.int32), 'num_e': num_e, 'R': R}
+    with ref_loader.cpu_patches():
+        for t in np.unique(quads[:, 3]):
+            g = ns.utils.get_big_graph(quads[quads[:, 3] == t][:, :3], R)
+            blob['g%d/id' % t] = g.ndata['id'].view(-1).numpy()
+            blob['g%d/norm' % t] = g.ndata['norm'].view(-1).numpy()
+            blob['g%d/src' % t] = g._src.numpy(); blob['g%d/dst' % t] = g._dst.numpy()
+            blob['g%d/type_s' % t] = g.edata['type_s'].numpy(); blob['g%d/type_o' % t] = g.edata['type_o'].numpy()
+        # make_subgraph: nodes {all ids of graph at t=24 except the first}
+        g = ns.utils.get_big_graph(quads[quads[:, 3] == 24][:, :3], R)
+        nodes = g.ndata['id'].view(-1).tolist()[1:]
+        sg = ns.utils.make_subgraph(g, nodes)
+        blob['sub/nodes'] = np.asarray(nodes)
+        blob['sub/id'] = sg.ndata['id'].view(-1).numpy(); blob['sub/norm'] = sg.ndata['norm'].view(-1).numpy()
+        blob['sub/src'] = sg._src.numpy(); blob['sub/dst'] = sg._dst.numpy()
+        blob['sub/type_s'] = sg.edata['type_s'].numpy()
+    S, ST, O, OT = restate.build_history(quads, num_e)
+    # history structure (validated against the reference's preprocessing loop semantics in the tests)
+    blob['hist_len_s'] = np.asarray([len(x) for x in S]); blob['hist_len_o'] = np.asarray([len(x) for x in O])
+    np.savez_compressed(os.path.join(OUT, 'graph_kats.npz'), **blob)
+    print('graph_kats.npz')
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_loader.load()
+    torch.manual_seed(0)
+    gen_layers(ns)
+    gen_graph_kats(ns)
+    gen_renet_tiny(ns)
+    gen_renet_icews18_slice(ns)

@@ -1,0 +1,107 @@
+"""-m "not gpu": the product's host-side batching (renet_b200.utils / graph / synthetic) against the
+oracle restatement of reference utils.py:68-93,115-181,209-244 and get_history_graph.py:142-190."""
+import numpy as np
+import torch
+
+from helpers import load_npz
+from oracle import restate
+from renet_b200 import synthetic, utils
+from renet_b200.graph import get_big_graph
+
+
+def _tiny():
+    quads, num_e, num_r = synthetic.make_quads('tiny', seed=3)
+    return quads, num_e, num_r
+
+
+def test_get_big_graph_matches_reference_golden():
+    b = load_npz('graph_kats.npz')
+    quads, R = b['quads'].astype(np.int64), int(b['R'])
+    for tt in np.unique(quads[:, 3]):
+        g = get_big_graph(quads[quads[:, 3] == tt][:, :3], R)
+        src, dst = g.edges()
+        np.testing.assert_array_equal(g.ndata['id'].view(-1).numpy(), b['g%d/id' % tt])
+        np.testing.assert_array_equal(src.numpy(), b['g%d/src' % tt])
+        np.testing.assert_array_equal(dst.numpy(), b['g%d/dst' % tt])
+        np.testing.assert_array_equal(g.edata['type_s'].numpy(), b['g%d/type_s' % tt])
+        np.testing.assert_array_equal(g.edata['type_o'].numpy(), b['g%d/type_o' % tt])
+        np.testing.assert_array_equal(g.ndata['norm'].view(-1).numpy(), b['g%d/norm' % tt])
+        assert g.ids == {int(e): i for i, e in enumerate(b['g%d/id' % tt])}
+        assert np.all(np.diff(g.dst) >= 0)      # destination-sorted copy
+
+
+def test_build_history_matches_oracle():
+    quads, num_e, _ = _tiny()
+    a = synthetic.build_history(quads)
+    b = restate.build_history(quads, num_e)
+    for x, y in zip(a, b):
+        assert len(x) == len(y)
+        for hx, hy in zip(x, y):
+            assert len(hx) == len(hy)
+            for ex, ey in zip(hx, hy):
+                np.testing.assert_array_equal(np.asarray(ex), np.asarray(ey))
+    assert max(len(h) for h in a[0]) == 10     # rolling window of 10 (get_history_graph.py:118)
+
+
+def _check_batch(quads, num_r, sel, col, hist, hist_t):
+    gd_p = synthetic.build_graph_dict(quads, num_r)
+    gd_o = restate.build_graph_dict(quads, num_r)
+    H, HT = [hist[i] for i in sel], [hist_t[i] for i in sel]
+    hb = utils.assemble_history_batch_host(H, HT, quads[sel][:, col], gd_p, sort=True)
+    bo = restate.assemble_batch(H, HT, quads[sel][:, col], sort=True)
+    go = restate.batch_graphs(bo, gd_o)
+    g = hb.graph
+    np.testing.assert_array_equal(hb.seq_len, bo.seq_len)
+    np.testing.assert_array_equal(hb.s_idx, bo.s_idx)
+    assert list(hb.times) == list(bo.times)
+    # nodes: same (component, entity) multiset; the product orders nodes by (component, entity id)
+    comp_of = np.repeat(np.arange(len(g['comp_sizes'])), g['comp_sizes'])
+    key_p = comp_of * 10 ** 6 + g['node_ent']
+    comp_o = np.repeat(np.arange(len(go.comp_sizes)), go.comp_sizes)
+    key_o = comp_o * 10 ** 6 + go.id
+    np.testing.assert_array_equal(np.sort(key_p), np.sort(key_o))
+    # per-node norm and per-edge (src key, dst key, type_s, type_o) multisets agree
+    order_p, order_o = np.argsort(key_p), np.argsort(key_o)
+    np.testing.assert_array_equal(g['norm'][order_p], go.norm[order_o])
+    dst_p = np.repeat(np.arange(len(key_p)), np.diff(g['row_ptr']))
+    ep = np.stack((key_p[g['col_src']], key_p[dst_p], g['col_type_s'], g['col_type_o']), 1)
+    eo = np.stack((key_o[go.src], key_o[go.dst], go.type_s, go.type_o), 1)
+    assert len(ep) == len(eo)
+    np.testing.assert_array_equal(ep[np.lexsort(ep.T[::-1])], eo[np.lexsort(eo.T[::-1])])
+    assert np.all(np.diff(dst_p) >= 0)
+    # read-out rows point at the same (component, entity)
+    np.testing.assert_array_equal(key_p[hb.readout_host], key_o[go.readout])
+    # packed order == torch's pack_padded_sequence
+    perm, bs = restate.packed_order(hb.seq_len)
+    np.testing.assert_array_equal(hb.batch_sizes, bs)
+    np.testing.assert_array_equal(hb.readout[5], perm)
+
+
+def test_assemble_history_batch_matches_oracle_tiny():
+    quads, num_e, num_r = _tiny()
+    S, ST, O, OT = synthetic.build_history(quads)
+    sel = np.arange(len(quads) - 120, len(quads))
+    _check_batch(quads, num_r, sel, 0, S, ST)
+    _check_batch(quads, num_r, sel, 2, O, OT)
+
+
+def test_assemble_history_batch_matches_oracle_icews18_shape():
+    quads, num_e, num_r = synthetic.make_quads('icews18', seed=5, num_timestamps=14)
+    S, ST, O, OT = synthetic.build_history(quads)
+    sel = np.random.RandomState(0).permutation(np.arange(len(quads) // 2, len(quads)))[:256]
+    _check_batch(quads, num_r, sel, 0, S, ST)
+    _check_batch(quads, num_r, sel, 2, O, OT)
+
+
+def test_empty_and_ragged_histories():
+    quads, num_e, num_r = _tiny()
+    S, ST, O, OT = synthetic.build_history(quads)
+    gd = synthetic.build_graph_dict(quads, num_r)
+    # first samples of the stream have empty histories; mix them with full ones
+    sel = np.concatenate((np.arange(0, 10), np.arange(len(quads) - 10, len(quads))))
+    hb = utils.assemble_history_batch_host([S[i] for i in sel], [ST[i] for i in sel], quads[sel][:, 0], gd)
+    assert hb.num_seq == sum(1 for i in sel if len(S[i]) > 0) < len(sel)
+    assert np.all(np.diff(hb.seq_len) <= 0)
+    # all-empty batch
+    hb = utils.assemble_history_batch_host([[], []], [[], []], np.asarray([1, 2]), gd)
+    assert hb.graph is None and hb.S == 0
