@@ -165,6 +165,25 @@ int renet_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_gl
                   int64_t S, int64_t Q, int64_t T, int32_t h,
                   void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Backward of renet_gru_fwd (the reference gets it from autograd through cuDNN's GRU and the concat
+ * loop).  dhn4/dhn3 [Q,h]: gradients of the two final hidden states.  fwd_workspace: the workspace
+ * renet_gru_fwd filled for the same inputs.  Outputs: dH2 [N,h] is WRITTEN (zero + scatter over
+ * readout); d_ent [*,h], d_rel [*,h], d_glob [T,h] (may be NULL) and the eight parameter gradients
+ * are ACCUMULATED (+=), like .grad. */
+int64_t renet_gru_bwd_workspace_bytes(int64_t S, int64_t Q, int64_t T, int32_t h);
+int renet_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
+                  const float* ent, const float* rel, const int32_t* seq_s, const int32_t* seq_r,
+                  const int32_t* seq_len, const int32_t* seq_start,
+                  const int32_t* host_batch_sizes, int32_t max_len,
+                  const float* w_ih4, const float* w_hh4, const float* w_ih3, const float* w_hh3,
+                  const float* dhn4, const float* dhn3,
+                  float* dH2, float* d_ent, float* d_rel, float* d_glob,
+                  float* dw_ih4, float* dw_hh4, float* db_ih4, float* db_hh4,
+                  float* dw_ih3, float* dw_hh3, float* db_ih3, float* db_hh3,
+                  int64_t N, int64_t S, int64_t Q, int64_t T, int32_t h,
+                  const void* fwd_workspace, void* bwd_workspace, int64_t bwd_workspace_bytes,
+                  void* stream);
+
 /* Materialise the packed GRU inputs exactly as the reference's aggregator returns them
  * (PackedSequence.data, time-major: Aggregator.py:160-165):  X4 [S,4h], X3 [S,3h];
  * packed_row [S] maps packed position -> sequence-major row. */

@@ -40,6 +40,15 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
                    int max_len, const float* w_ih4, const float* w_hh4, const float* b_ih4, const float* b_hh4,
                    const float* w_ih3, const float* w_hh3, const float* b_ih3, const float* b_hh3, float* hn4,
                    float* hn3, int64_t S, int64_t Q, int64_t T, int h, float* ws_base, cudaStream_t stream);
+int64_t gru_bwd_workspace_floats(int64_t S, int64_t Q, int64_t T, int h);
+int launch_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
+                   const float* ent, const float* rel, const int32_t* seq_s, const int32_t* seq_r,
+                   const int32_t* seq_len, const int32_t* seq_start, const int32_t* host_batch_sizes, int max_len,
+                   const float* w_ih4, const float* w_hh4, const float* w_ih3, const float* w_hh3,
+                   const float* dhn4, const float* dhn3, float* dH2, float* d_ent, float* d_rel, float* d_glob,
+                   float* dw_ih4, float* dw_hh4, float* db_ih4, float* db_hh4, float* dw_ih3, float* dw_hh3,
+                   float* db_ih3, float* db_hh3, int64_t N, int64_t S, int64_t Q, int64_t T, int h,
+                   const float* fwd_ws, float* bwd_ws, cudaStream_t stream);
 int launch_pack_inputs(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
                        const float* ent, const float* rel, const int32_t* row_seq, const int32_t* seq_s,
                        const int32_t* seq_r, const int32_t* packed_row, float* X4, float* X3, int64_t S, int h,
@@ -228,6 +237,34 @@ int renet_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_gl
   return launch_gru_fwd(H2, readout, row_glob, glob, ent, rel, seq_s, seq_r, seq_len, seq_start, host_batch_sizes,
                         max_len, w_ih4, w_hh4, b_ih4, b_hh4, w_ih3, w_hh3, b_ih3, b_hh3, hn4, hn3, S, Q, T, h,
                         (float*)workspace, (cudaStream_t)stream);
+}
+
+int64_t renet_gru_bwd_workspace_bytes(int64_t S, int64_t Q, int64_t T, int32_t h) {
+  return gru_bwd_workspace_floats(S, Q, T, h) * (int64_t)sizeof(float);
+}
+
+int renet_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
+                  const float* ent, const float* rel, const int32_t* seq_s, const int32_t* seq_r,
+                  const int32_t* seq_len, const int32_t* seq_start, const int32_t* host_batch_sizes,
+                  int32_t max_len, const float* w_ih4, const float* w_hh4, const float* w_ih3, const float* w_hh3,
+                  const float* dhn4, const float* dhn3, float* dH2, float* d_ent, float* d_rel, float* d_glob,
+                  float* dw_ih4, float* dw_hh4, float* db_ih4, float* db_hh4, float* dw_ih3, float* dw_hh3,
+                  float* db_ih3, float* db_hh3, int64_t N, int64_t S, int64_t Q, int64_t T, int32_t h,
+                  const void* fwd_workspace, void* bwd_workspace, int64_t bwd_workspace_bytes, void* stream) {
+  RENET_CHECK_ARG(N >= 0 && S >= 0 && Q >= 0 && T >= 0 && h > 0 && max_len >= 0, "renet_gru_bwd: bad shape");
+  if (S == 0 || Q == 0) return RENET_OK;
+  RENET_CHECK_ARG(H2 && readout && row_glob && glob && ent && rel && seq_s && seq_r && seq_len && seq_start &&
+                      host_batch_sizes && w_ih4 && w_hh4 && w_ih3 && w_hh3 && dhn4 && dhn3 && dH2 && d_ent &&
+                      d_rel && dw_ih4 && dw_hh4 && db_ih4 && db_hh4 && dw_ih3 && dw_hh3 && db_ih3 && db_hh3 &&
+                      fwd_workspace && bwd_workspace,
+                  "renet_gru_bwd: null pointer");
+  RENET_CHECK_ARG(bwd_workspace_bytes >= renet_gru_bwd_workspace_bytes(S, Q, T, h),
+                  "renet_gru_bwd: workspace too small");
+  RENET_CHECK_ARG((reinterpret_cast<uintptr_t>(bwd_workspace) & 15) == 0, "renet_gru_bwd: workspace must be 16-byte aligned");
+  return launch_gru_bwd(H2, readout, row_glob, glob, ent, rel, seq_s, seq_r, seq_len, seq_start, host_batch_sizes,
+                        max_len, w_ih4, w_hh4, w_ih3, w_hh3, dhn4, dhn3, dH2, d_ent, d_rel, d_glob, dw_ih4, dw_hh4,
+                        db_ih4, db_hh4, dw_ih3, dw_hh3, db_ih3, db_hh3, N, S, Q, T, h, (const float*)fwd_workspace,
+                        (float*)bwd_workspace, (cudaStream_t)stream);
 }
 
 int renet_pack_inputs(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,

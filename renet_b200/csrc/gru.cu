@@ -122,7 +122,7 @@ GruWs carve(float* base, int64_t S, int64_t Q, int64_t T, int h, int max_len) {
   w.GI = take(S * 6 * h);
   w.PQ = take(Q * 6 * h);
   w.PT = take(T * 6 * h);
-  w.GH = take(Q * 6 * h);
+  w.GH = take((int64_t)max_len * Q * 6 * h);   // recurrent pre-activations of every step (kept for backward)
   w.Hs = take((int64_t)(max_len + 1) * Q * 2 * h);
   w.total_floats = off;
   return w;
@@ -194,17 +194,264 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
     if (n_act <= 0) break;
     const float* Hprev = (t == 0) ? nullptr : w.Hs + (int64_t)t * hs_stride;
     float* Hnext = w.Hs + (int64_t)(t + 1) * hs_stride;
+    float* GH = w.GH + (int64_t)t * Q * 6 * h;
     if (t > 0) {
-      if ((rc = sgemm_nn(Hprev, nullptr, 2 * h, w.Whh, 6 * h, w.GH, 6 * h, nullptr, n_act, 3 * h, h, false, stream)))
+      if ((rc = sgemm_nn(Hprev, nullptr, 2 * h, w.Whh, 6 * h, GH, 6 * h, nullptr, n_act, 3 * h, h, false, stream)))
         return rc;
-      if ((rc = sgemm_nn(Hprev + h, nullptr, 2 * h, w.Whh + 3 * h, 6 * h, w.GH + 3 * h, 6 * h, nullptr, n_act,
+      if ((rc = sgemm_nn(Hprev + h, nullptr, 2 * h, w.Whh + 3 * h, 6 * h, GH + 3 * h, 6 * h, nullptr, n_act,
                          3 * h, h, false, stream)))
         return rc;
     }
     const int total = n_act * 2 * h;
-    gru_gate_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w.GI, w.PQ, w.PT, w.GH, w.bhh, row_glob, seq_start,
+    gru_gate_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w.GI, w.PQ, w.PT, GH, w.bhh, row_glob, seq_start,
                                                             seq_len, Hprev, Hnext, hn4, hn3, n_act, h, t);
     RENET_CHECK_LAUNCH("gru_gate_kernel");
+  }
+  return RENET_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------------
+namespace {
+
+// One reverse time step for both encoders.  Thread = (q < n_act, encoder, unit).
+//   dh   : gradient w.r.t. the state AFTER step t: from dHcur for q < n_next (sequences that continue),
+//          from dhn4/dhn3 for n_next <= q < n_act (sequences whose last step is t)
+//   out  : dGI[row] (3 gates), dGH[q] (3 gates), dHprev[q] = dh * z  (the W_hh part is added by a GEMM)
+__global__ void gru_gate_bwd_kernel(const float* __restrict__ GI, const float* __restrict__ PQ,
+                                    const float* __restrict__ PT, const float* __restrict__ GH,
+                                    const float* __restrict__ bhh, const int32_t* __restrict__ row_glob,
+                                    const int32_t* __restrict__ seq_start, const float* __restrict__ Hprev,
+                                    const float* __restrict__ dHcur, const float* __restrict__ dhn4,
+                                    const float* __restrict__ dhn3, float* __restrict__ dGI,
+                                    float* __restrict__ dGH, float* __restrict__ dHprev, int n_act, int n_next,
+                                    int h, int t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_q = 2 * h;
+  if (i >= n_act * per_q) return;
+  const int q = i / per_q, c = i % per_q;
+  const int enc = c / h, u = c % h;
+  const int64_t row = (int64_t)seq_start[q] + t;
+  const int64_t g = (int64_t)row_glob[row];
+  const int base = enc * 3 * h + u;
+  const float* gi = GI + row * 6 * h + base;
+  const float* pq = PQ + (int64_t)q * 6 * h + base;
+  const float* pt = PT + g * 6 * h + base;
+  const float i_r = gi[0] + pq[0] + pt[0];
+  const float i_z = gi[h] + pq[h] + pt[h];
+  const float i_n = gi[2 * h] + pq[2 * h] + pt[2 * h];
+  float h_r = bhh[base], h_z = bhh[base + h], h_n = bhh[base + 2 * h], hp = 0.f;
+  if (Hprev != nullptr) {
+    const float* gh = GH + (int64_t)q * 6 * h + base;
+    h_r += gh[0]; h_z += gh[h]; h_n += gh[2 * h];
+    hp = Hprev[(int64_t)q * per_q + c];
+  }
+  const float r = sigmoidf_(i_r + h_r);
+  const float z = sigmoidf_(i_z + h_z);
+  const float n = tanhf(i_n + r * h_n);
+  const float dh = (q < n_next) ? dHcur[(int64_t)q * per_q + c]
+                                : (enc == 0 ? dhn4 : dhn3)[(int64_t)q * h + u];
+  const float dn = dh * (1.f - z);
+  const float dz = dh * (hp - n);
+  const float dpre_n = dn * (1.f - n * n);
+  const float dpre_z = dz * z * (1.f - z);
+  const float dr = dpre_n * h_n;
+  const float dpre_r = dr * r * (1.f - r);
+  float* o = dGI + row * 6 * h + base;
+  o[0] = dpre_r; o[h] = dpre_z; o[2 * h] = dpre_n;
+  float* o2 = dGH + (int64_t)q * 6 * h + base;
+  o2[0] = dpre_r; o2[h] = dpre_z; o2[2 * h] = dpre_n * r;
+  dHprev[(int64_t)q * per_q + c] = dh * z;
+}
+
+// out[c] += sum_{r < n} X[r*ld + c]   (grid: column blocks x row chunks; one atomic per thread)
+__global__ void colsum_accum_kernel(const float* __restrict__ X, int64_t ld, int64_t n, int cols,
+                                    float* __restrict__ out, int rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(n, r0 + rows_per_block);
+  float s = 0.f;
+  for (int64_t r = r0; r < r1; ++r) s += X[r * ld + c];
+  atomicAdd(out + c, s);
+}
+
+// dPQ[q, :] = sum over the rows of sequence q of dGI[row, :]
+__global__ void seq_rowsum_kernel(const float* __restrict__ dGI, const int32_t* __restrict__ seq_start,
+                                  const int32_t* __restrict__ seq_len, float* __restrict__ dPQ, int cols) {
+  const int q = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const int64_t r0 = seq_start[q];
+  const int len = seq_len[q];
+  float s = 0.f;
+  for (int t = 0; t < len; ++t) s += dGI[(r0 + t) * cols + c];
+  dPQ[(int64_t)q * cols + c] = s;
+}
+
+// dst[o, dst_off + k] += src[k, src_off + o]   (inverse of pack_transpose_kernel, accumulating)
+__global__ void unpack_transpose_add_kernel(const float* __restrict__ src, int ld_src, int src_off, int rows_dst,
+                                            float* __restrict__ dst, int ld_dst, int dst_off, int h) {
+  __shared__ float tile[32][33];
+  const int o0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    int k = k0 + i, o = o0 + tx;
+    tile[i][tx] = (o < rows_dst && k < h) ? src[(int64_t)k * ld_src + src_off + o] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    int o = o0 + i, k = k0 + tx;
+    if (o < rows_dst && k < h) dst[(int64_t)o * ld_dst + dst_off + k] += tile[tx][i];
+  }
+}
+
+struct GruBwdWs {
+  float *dGI, *dGH, *dPQ, *dPT, *dHa, *dHb, *dBrow, *dBent, *dBrel, *dBglob, *dWhh, *dRows, *dQ, *dbias;
+  int64_t total_floats;
+};
+
+GruBwdWs carve_bwd(float* base, int64_t S, int64_t Q, int64_t T, int h) {
+  GruBwdWs w;
+  int64_t off = 0;
+  auto take = [&](int64_t n) { float* p = base ? base + off : nullptr; off += align4(n); return p; };
+  w.dGI = take(S * 6 * h);
+  w.dGH = take(Q * 6 * h);
+  w.dPQ = take(Q * 6 * h);
+  w.dPT = take(T * 6 * h);
+  w.dHa = take(Q * 2 * h);
+  w.dHb = take(Q * 2 * h);
+  w.dBrow = take((int64_t)h * 6 * h);
+  w.dBent = take((int64_t)h * 6 * h);
+  w.dBrel = take((int64_t)h * 3 * h);
+  w.dBglob = take((int64_t)h * 6 * h);
+  w.dWhh = take((int64_t)h * 6 * h);
+  w.dRows = take(S * h);
+  w.dQ = take(Q * h);
+  w.dbias = take(12 * h);
+  w.total_floats = off;
+  return w;
+}
+
+}  // namespace
+
+int64_t gru_bwd_workspace_floats(int64_t S, int64_t Q, int64_t T, int h) {
+  return carve_bwd(nullptr, S, Q, T, h).total_floats;
+}
+
+int launch_scatter_add_rows(const float* src, const int32_t* index, float* dst, int64_t n_rows, int d,
+                            cudaStream_t stream);
+
+int launch_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
+                   const float* ent, const float* rel, const int32_t* seq_s, const int32_t* seq_r,
+                   const int32_t* seq_len, const int32_t* seq_start, const int32_t* host_batch_sizes, int max_len,
+                   const float* w_ih4, const float* w_hh4, const float* w_ih3, const float* w_hh3,
+                   const float* dhn4, const float* dhn3, float* dH2, float* d_ent, float* d_rel, float* d_glob,
+                   float* dw_ih4, float* dw_hh4, float* db_ih4, float* db_hh4, float* dw_ih3, float* dw_hh3,
+                   float* db_ih3, float* db_hh3, int64_t N, int64_t S, int64_t Q, int64_t T, int h,
+                   const float* fwd_ws, float* bwd_ws, cudaStream_t stream) {
+  GruWs f = carve(const_cast<float*>(fwd_ws), S, Q, T, h, kMaxLenWs);
+  GruBwdWs b = carve_bwd(bwd_ws, S, Q, T, h);
+  int rc;
+  RENET_CHECK_CUDA(cudaMemsetAsync(b.dbias, 0, 12 * h * sizeof(float), stream));
+  RENET_CHECK_CUDA(cudaMemsetAsync(b.dWhh, 0, (int64_t)h * 6 * h * sizeof(float), stream));
+  RENET_CHECK_CUDA(cudaMemsetAsync(b.dPT, 0, T * 6 * h * sizeof(float), stream));
+  RENET_CHECK_CUDA(cudaMemsetAsync(dH2, 0, N * h * sizeof(float), stream));
+  int last = 0;
+  while (last < max_len && host_batch_sizes[last] > 0) ++last;
+  const int64_t hs_stride = Q * 2 * h;
+  float* dHcur = b.dHa;
+  float* dHprev = b.dHb;
+  for (int t = last - 1; t >= 0; --t) {
+    const int n_act = host_batch_sizes[t];
+    const int n_next = (t + 1 < last) ? host_batch_sizes[t + 1] : 0;
+    const float* Hprev = (t == 0) ? nullptr : f.Hs + (int64_t)t * hs_stride;
+    const float* GH = f.GH + (int64_t)t * Q * 6 * h;
+    const int total = n_act * 2 * h;
+    gru_gate_bwd_kernel<<<(total + 255) / 256, 256, 0, stream>>>(f.GI, f.PQ, f.PT, GH, f.bhh, row_glob, seq_start,
+                                                                Hprev, dHcur, dhn4, dhn3, b.dGI, b.dGH, dHprev,
+                                                                n_act, n_next, h, t);
+    RENET_CHECK_LAUNCH("gru_gate_bwd_kernel");
+    // db_hh += colsum(dGH[0:n_act])
+    {
+      const int rpb = 64;
+      dim3 grid((6 * h + 127) / 128, (n_act + rpb - 1) / rpb);
+      colsum_accum_kernel<<<grid, 128, 0, stream>>>(b.dGH, 6 * h, n_act, 6 * h, b.dbias + 6 * h, rpb);
+      RENET_CHECK_LAUNCH("colsum_accum_kernel");
+    }
+    if (t > 0) {
+      // dHprev += dGH_enc @ w_hh_enc   ([n,3h] @ [3h,h])
+      if ((rc = sgemm_nn(b.dGH, nullptr, 6 * h, w_hh4, h, dHprev, 2 * h, nullptr, n_act, h, 3 * h, true, stream))) return rc;
+      if ((rc = sgemm_nn(b.dGH + 3 * h, nullptr, 6 * h, w_hh3, h, dHprev + h, 2 * h, nullptr, n_act, h, 3 * h, true, stream))) return rc;
+      // dWhh[k, o] += Hprev[:, k]^T dGH[:, o]   (packed [h, 6h] like Whh)
+      if ((rc = sgemm_tn(Hprev, nullptr, 2 * h, b.dGH, 6 * h, b.dWhh, 6 * h, h, 3 * h, n_act, true, stream))) return rc;
+      if ((rc = sgemm_tn(Hprev + h, nullptr, 2 * h, b.dGH + 3 * h, 6 * h, b.dWhh + 3 * h, 6 * h, h, 3 * h, n_act, true, stream))) return rc;
+    }
+    float* tmp = dHcur; dHcur = dHprev; dHprev = tmp;
+  }
+  // ---- biases of the input projection: every row carries b_ih once ------------------------------------
+  {
+    const int rpb = 128;
+    dim3 grid((6 * h + 127) / 128, (unsigned)((S + rpb - 1) / rpb));
+    colsum_accum_kernel<<<grid, 128, 0, stream>>>(b.dGI, 6 * h, S, 6 * h, b.dbias, rpb);
+    RENET_CHECK_LAUNCH("colsum_accum_kernel");
+  }
+  // ---- per-sequence and per-timestamp sums of dGI --------------------------------------------------------
+  {
+    dim3 grid((6 * h + 127) / 128, (unsigned)Q);
+    seq_rowsum_kernel<<<grid, 128, 0, stream>>>(b.dGI, seq_start, seq_len, b.dPQ, 6 * h);
+    RENET_CHECK_LAUNCH("seq_rowsum_kernel");
+  }
+  if ((rc = launch_scatter_add_rows(b.dGI, row_glob, b.dPT, S, 6 * h, stream))) return rc;
+  // ---- packed weight gradients: dB = X^T @ dG ----------------------------------------------------------------
+  if ((rc = sgemm_tn(H2, readout, h, b.dGI, 6 * h, b.dBrow, 6 * h, h, 6 * h, S, false, stream))) return rc;
+  if ((rc = sgemm_tn(ent, seq_s, h, b.dPQ, 6 * h, b.dBent, 6 * h, h, 6 * h, Q, false, stream))) return rc;
+  if ((rc = sgemm_tn(rel, seq_r, h, b.dPQ, 6 * h, b.dBrel, 3 * h, h, 3 * h, Q, false, stream))) return rc;
+  if ((rc = sgemm_tn(glob, nullptr, h, b.dPT, 6 * h, b.dBglob, 6 * h, h, 6 * h, T, false, stream))) return rc;
+  const dim3 tb(32, 8);
+  auto unpack = [&](const float* src, int ld_src, int src_off, float* dst, int ld_dst, int dst_off) -> int {
+    dim3 grid((3 * h + 31) / 32, (h + 31) / 32);
+    unpack_transpose_add_kernel<<<grid, tb, 0, stream>>>(src, ld_src, src_off, 3 * h, dst, ld_dst, dst_off, h);
+    RENET_CHECK_LAUNCH("unpack_transpose_add_kernel");
+    return RENET_OK;
+  };
+  if ((rc = unpack(b.dBrow, 6 * h, 0, dw_ih4, 4 * h, 0))) return rc;
+  if ((rc = unpack(b.dBrow, 6 * h, 3 * h, dw_ih3, 3 * h, 0))) return rc;
+  if ((rc = unpack(b.dBent, 6 * h, 0, dw_ih4, 4 * h, h))) return rc;
+  if ((rc = unpack(b.dBent, 6 * h, 3 * h, dw_ih3, 3 * h, h))) return rc;
+  if ((rc = unpack(b.dBrel, 3 * h, 0, dw_ih4, 4 * h, 2 * h))) return rc;
+  if ((rc = unpack(b.dBglob, 6 * h, 0, dw_ih4, 4 * h, 3 * h))) return rc;
+  if ((rc = unpack(b.dBglob, 6 * h, 3 * h, dw_ih3, 3 * h, 2 * h))) return rc;
+  if ((rc = unpack(b.dWhh, 6 * h, 0, dw_hh4, h, 0))) return rc;
+  if ((rc = unpack(b.dWhh, 6 * h, 3 * h, dw_hh3, h, 0))) return rc;
+  // biases: dbias = [db_ih4 | db_ih3 | db_hh4 | db_hh3]
+  {
+    float* outs[4] = {db_ih4, db_ih3, db_hh4, db_hh3};
+    for (int k = 0; k < 4; ++k) {
+      const int rpb = 1;
+      dim3 grid((3 * h + 127) / 128, 1);
+      colsum_accum_kernel<<<grid, 128, 0, stream>>>(b.dbias + (int64_t)k * 3 * h, 3 * h, 1, 3 * h, outs[k], rpb);
+      RENET_CHECK_LAUNCH("colsum_accum_kernel");
+    }
+  }
+  // ---- input gradients: dX = dG @ W_ih[:, block] ------------------------------------------------------------------
+  // read-out rows -> dH2
+  if ((rc = sgemm_nn(b.dGI, nullptr, 6 * h, w_ih4, 4 * h, b.dRows, h, nullptr, S, h, 3 * h, false, stream))) return rc;
+  if ((rc = sgemm_nn(b.dGI + 3 * h, nullptr, 6 * h, w_ih3, 3 * h, b.dRows, h, nullptr, S, h, 3 * h, true, stream))) return rc;
+  if ((rc = launch_scatter_add_rows(b.dRows, readout, dH2, S, h, stream))) return rc;
+  // ent[s_q]
+  if ((rc = sgemm_nn(b.dPQ, nullptr, 6 * h, w_ih4 + h, 4 * h, b.dQ, h, nullptr, Q, h, 3 * h, false, stream))) return rc;
+  if ((rc = sgemm_nn(b.dPQ + 3 * h, nullptr, 6 * h, w_ih3 + h, 3 * h, b.dQ, h, nullptr, Q, h, 3 * h, true, stream))) return rc;
+  if ((rc = launch_scatter_add_rows(b.dQ, seq_s, d_ent, Q, h, stream))) return rc;
+  // rel[r_q]
+  if ((rc = sgemm_nn(b.dPQ, nullptr, 6 * h, w_ih4 + 2 * h, 4 * h, b.dQ, h, nullptr, Q, h, 3 * h, false, stream))) return rc;
+  if ((rc = launch_scatter_add_rows(b.dQ, seq_r, d_rel, Q, h, stream))) return rc;
+  // glob[t]
+  if (d_glob != nullptr) {
+    if ((rc = sgemm_nn(b.dPT, nullptr, 6 * h, w_ih4 + 3 * h, 4 * h, d_glob, h, nullptr, T, h, 3 * h, true, stream))) return rc;
+    if ((rc = sgemm_nn(b.dPT + 3 * h, nullptr, 6 * h, w_ih3 + 2 * h, 3 * h, d_glob, h, nullptr, T, h, 3 * h, true, stream))) return rc;
   }
   return RENET_OK;
 }
