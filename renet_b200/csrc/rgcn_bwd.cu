@@ -11,6 +11,7 @@
 // ICEWS18 edges): edges are grouped by relation, each warp reduces a run of edges in registers and
 // flushes once per relation change with 128-bit vector REDs.
 #include "common.cuh"
+#include "rgcn_tile.cuh"
 
 namespace renet {
 namespace {
@@ -50,66 +51,34 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
   }
 }
 
-// dH[u] = dH[u] (loop part, already there when HAS_LOOP) + sum over out-edges of W^T (norm[dst] P[dst])
+// dH[u] = dH[u] (loop part, already there when HAS_LOOP) + sum over out-edges of W^T (norm[dst] P[dst]).
+// Tile kernel (rgcn_tile.cuh): 16 source rows per CTA, the out-edge range split evenly
+// over the warps; transposed 2x2 blocks, per-edge scale norm[dst].
 template <bool HAS_LOOP>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
-rgcn_dh_d200_kernel(const float* __restrict__ P, const float* __restrict__ W, const int32_t* __restrict__ t_row_ptr,
+__global__ void __launch_bounds__(kTileWarps * 32)
+rgcn_dh_tile_kernel(const float* __restrict__ P, const float* __restrict__ W, const int32_t* __restrict__ t_row_ptr,
                     const int32_t* __restrict__ t_col_dst, const int32_t* __restrict__ t_col_type,
                     const float* __restrict__ norm, float* __restrict__ dH, int N) {
-  const int lane = threadIdx.x & 31;
-  const int u = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-  if (u >= N) return;
-  const int beg = __ldg(t_row_ptr + u), end = __ldg(t_row_ptr + u + 1);
-  const bool active = lane < 25;
-  const int foff = lane * 8, woff = lane * 16;
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int base = beg; base < end; base += 32) {
-    const int e = base + lane;
-    int my_d = 0, my_t = 0;
-    float my_n = 0.f;
-    if (e < end) {
-      my_d = __ldg(t_col_dst + e);
-      my_t = __ldg(t_col_type + e);
-      my_n = __ldg(norm + my_d);
+  __shared__ __align__(16) float agg[kTileNodes][200];
+  __shared__ int s_rp[kTileNodes + 1];
+  const int tid = threadIdx.x;
+  const int v0 = blockIdx.x * kTileNodes;
+  const int nv = min(kTileNodes, N - v0);
+  for (int i = tid; i < kTileNodes * 200; i += kTileWarps * 32) (&agg[0][0])[i] = 0.f;
+  if (tid <= nv) s_rp[tid] = __ldg(t_row_ptr + v0 + tid);
+  __syncthreads();
+  tile_accumulate<true, false, true>(agg, s_rp, nv, P, nullptr, W, t_col_dst, t_col_type, norm);
+  __syncthreads();
+  for (int i = tid; i < nv * 100; i += kTileWarps * 32) {
+    const int r = i / 100, c = (i % 100) * 2;
+    float2 o = *reinterpret_cast<const float2*>(&agg[r][c]);
+    float* op = dH + (int64_t)(v0 + r) * 200 + c;
+    if (HAS_LOOP) {
+      const float2 l = *reinterpret_cast<const float2*>(op);
+      o.x += l.x; o.y += l.y;
     }
-    const int cnt = min(32, end - base);
-#pragma unroll 2
-    for (int j = 0; j < cnt; ++j) {
-      const int d = __shfl_sync(0xffffffffu, my_d, j);
-      const int t = __shfl_sync(0xffffffffu, my_t, j);
-      const float sc = __shfl_sync(0xffffffffu, my_n, j);
-      if (active) {
-        const float* gp = P + (int64_t)d * 200 + foff;
-        const float* wp = W + (int64_t)t * 400 + woff;
-        float4 g0 = ldg_f4_stream(gp), g1 = ldg_f4_stream(gp + 4);
-        const float4 w0 = ldg_f4(wp), w1 = ldg_f4(wp + 4), w2 = ldg_f4(wp + 8), w3 = ldg_f4(wp + 12);
-        g0.x *= sc; g0.y *= sc; g0.z *= sc; g0.w *= sc;
-        g1.x *= sc; g1.y *= sc; g1.z *= sc; g1.w *= sc;
-        // dh[b*2+i] += sum_j W[b][i][j] * g[b*2+j]   with W[b] = (x y; z w)
-        acc[0] = fmaf(g0.x, w0.x, fmaf(g0.y, w0.y, acc[0]));
-        acc[1] = fmaf(g0.x, w0.z, fmaf(g0.y, w0.w, acc[1]));
-        acc[2] = fmaf(g0.z, w1.x, fmaf(g0.w, w1.y, acc[2]));
-        acc[3] = fmaf(g0.z, w1.z, fmaf(g0.w, w1.w, acc[3]));
-        acc[4] = fmaf(g1.x, w2.x, fmaf(g1.y, w2.y, acc[4]));
-        acc[5] = fmaf(g1.x, w2.z, fmaf(g1.y, w2.w, acc[5]));
-        acc[6] = fmaf(g1.z, w3.x, fmaf(g1.w, w3.y, acc[6]));
-        acc[7] = fmaf(g1.z, w3.z, fmaf(g1.w, w3.w, acc[7]));
-      }
-    }
+    *reinterpret_cast<float2*>(op) = o;
   }
-  if (!active) return;
-  float* op = dH + (int64_t)u * 200 + foff;
-  float4 o0 = make_float4(acc[0], acc[1], acc[2], acc[3]);
-  float4 o1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
-  if (HAS_LOOP) {
-    const float4 l0 = *reinterpret_cast<const float4*>(op), l1 = *reinterpret_cast<const float4*>(op + 4);
-    o0.x += l0.x; o0.y += l0.y; o0.z += l0.z; o0.w += l0.w;
-    o1.x += l1.x; o1.y += l1.y; o1.z += l1.z; o1.w += l1.w;
-  }
-  st_f4(op, o0);
-  st_f4(op + 4, o1);
 }
 
 __global__ void rgcn_dh_generic_kernel(const float* __restrict__ P, const float* __restrict__ W,
@@ -303,12 +272,12 @@ int launch_rgcn_bwd(const float* H, const int32_t* h_index, const float* W, cons
                     ((reinterpret_cast<uintptr_t>(H) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(dH) |
                       reinterpret_cast<uintptr_t>(dW) | reinterpret_cast<uintptr_t>(P)) & 15) == 0;
   if (fast) {
-    const unsigned grid = (unsigned)((N + kWarpsPerCta - 1) / kWarpsPerCta);
+    const unsigned grid = (unsigned)((N + kTileNodes - 1) / kTileNodes);
     if (Wloop != nullptr)
-      rgcn_dh_d200_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(P, W, t_row_ptr, t_col_dst, t_col_type, norm, dH, (int)N);
+      rgcn_dh_tile_kernel<true><<<grid, kTileWarps * 32, 0, stream>>>(P, W, t_row_ptr, t_col_dst, t_col_type, norm, dH, (int)N);
     else
-      rgcn_dh_d200_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(P, W, t_row_ptr, t_col_dst, t_col_type, norm, dH, (int)N);
-    RENET_CHECK_LAUNCH("rgcn_dh_d200_kernel");
+      rgcn_dh_tile_kernel<false><<<grid, kTileWarps * 32, 0, stream>>>(P, W, t_row_ptr, t_col_dst, t_col_type, norm, dH, (int)N);
+    RENET_CHECK_LAUNCH("rgcn_dh_tile_kernel");
     const int64_t warps = (E + kEdgesPerWarp - 1) / kEdgesPerWarp;
     const unsigned g2 = (unsigned)((warps + kWarpsPerCta - 1) / kWarpsPerCta);
     if (h_index)

@@ -8,89 +8,49 @@
 // destination-sorted CSR: no per-edge message ever reaches memory and no atomics are needed.
 //
 // Fast path (d_in = d_out = 200, num_bases = 100, 2x2 blocks -- the only shape RE-Net uses,
-// model.py:36): one warp per destination node.  Lanes 0..24 own 8 features (= 4 blocks) each:
-// per edge a lane issues 2 x LDG.128 on the 800 B source row (streamed, L1::no_allocate) and
-// 4 x LDG.128 on the 1600 B relation block table row (L1-allocating: the table is 819 KB, the hot
-// relations stay in L1).  Edge indices are fetched 32 at a time, coalesced, and broadcast with
-// shuffles so the gathers of several edges are in flight together.
+// model.py:36): see rgcn_tile.cuh.  One CTA = 16 destination rows, edges split evenly over 8 warps,
+// warp-level segmented reduction into a shared tile, fused norm / self-loop / activation epilogue.
 #include "common.cuh"
+#include "rgcn_tile.cuh"
 
 namespace renet {
 namespace {
 
-constexpr int kWarpsPerCta = 8;
-
 template <bool RELU, bool HAS_LOOP, bool INDEXED>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kTileWarps * 32)
 rgcn_gather_d200_kernel(const float* __restrict__ H, const int32_t* __restrict__ h_index,
                         const float* __restrict__ W, const int32_t* __restrict__ row_ptr,
                         const int32_t* __restrict__ col_src, const int32_t* __restrict__ col_type,
                         const float* __restrict__ norm, float* __restrict__ Hout, int N, int passthrough) {
-  const int lane = threadIdx.x & 31;
-  const int v = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-  if (v >= N) return;
-  const int beg = __ldg(row_ptr + v), end = __ldg(row_ptr + v + 1);
-  const bool active = lane < 25;
-  const int foff = lane * 8;    // first feature owned by this lane
-  const int woff = lane * 16;   // first weight of the lane's 4 blocks
-
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-
-  for (int base = beg; base < end; base += 32) {
-    const int e = base + lane;
-    int my_s = 0, my_t = 0;
-    if (e < end) {
-      my_s = __ldg(col_src + e);
-      my_t = __ldg(col_type + e);
-      if (INDEXED) my_s = __ldg(h_index + my_s);
+  __shared__ __align__(16) float agg[kTileNodes][200];
+  __shared__ int s_rp[kTileNodes + 1];
+  const int tid = threadIdx.x;
+  const int v0 = blockIdx.x * kTileNodes;
+  const int nv = min(kTileNodes, N - v0);
+  for (int i = tid; i < kTileNodes * 200; i += kTileWarps * 32) (&agg[0][0])[i] = 0.f;
+  if (tid <= nv) s_rp[tid] = __ldg(row_ptr + v0 + tid);
+  __syncthreads();
+  tile_accumulate<false, INDEXED, false>(agg, s_rp, nv, H, h_index, W, col_src, col_type, nullptr);
+  __syncthreads();
+  // epilogue: nv rows x 100 float2, coalesced
+  for (int i = tid; i < nv * 100; i += kTileWarps * 32) {
+    const int r = i / 100, c = (i % 100) * 2;
+    const int v = v0 + r;
+    float2 a = *reinterpret_cast<const float2*>(&agg[r][c]);
+    if (passthrough) {  // graph without edges: DGL 0.4 skips the reduce, h is left as is
+      const int64_t hr = INDEXED ? (int64_t)__ldg(h_index + v) : v;
+      a = *reinterpret_cast<const float2*>(H + hr * 200 + c);
     }
-    const int cnt = min(32, end - base);
-#pragma unroll 2
-    for (int j = 0; j < cnt; ++j) {
-      const int s = __shfl_sync(0xffffffffu, my_s, j);
-      const int t = __shfl_sync(0xffffffffu, my_t, j);
-      if (active) {
-        const float* hp = H + (int64_t)s * 200 + foff;
-        const float* wp = W + (int64_t)t * 400 + woff;
-        const float4 h0 = ldg_f4_stream(hp), h1 = ldg_f4_stream(hp + 4);
-        const float4 w0 = ldg_f4(wp), w1 = ldg_f4(wp + 4), w2 = ldg_f4(wp + 8), w3 = ldg_f4(wp + 12);
-        // block layout W[b][i][j] = w[b*4 + i*2 + j];  out[b*2+j] += in[b*2+0]*W[b][0][j] + in[b*2+1]*W[b][1][j]
-        acc[0] = fmaf(h0.x, w0.x, fmaf(h0.y, w0.z, acc[0]));
-        acc[1] = fmaf(h0.x, w0.y, fmaf(h0.y, w0.w, acc[1]));
-        acc[2] = fmaf(h0.z, w1.x, fmaf(h0.w, w1.z, acc[2]));
-        acc[3] = fmaf(h0.z, w1.y, fmaf(h0.w, w1.w, acc[3]));
-        acc[4] = fmaf(h1.x, w2.x, fmaf(h1.y, w2.z, acc[4]));
-        acc[5] = fmaf(h1.x, w2.y, fmaf(h1.y, w2.w, acc[5]));
-        acc[6] = fmaf(h1.z, w3.x, fmaf(h1.w, w3.z, acc[6]));
-        acc[7] = fmaf(h1.z, w3.y, fmaf(h1.w, w3.w, acc[7]));
-      }
+    const float nvv = __ldg(norm + v);
+    float* op = Hout + (int64_t)v * 200 + c;
+    float2 o = make_float2(a.x * nvv, a.y * nvv);
+    if (HAS_LOOP) {
+      const float2 l = *reinterpret_cast<const float2*>(op);
+      o.x += l.x; o.y += l.y;
     }
+    if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
+    *reinterpret_cast<float2*>(op) = o;
   }
-
-  if (!active) return;
-  if (passthrough) {  // graph without edges: DGL 0.4 skips the reduce, h is left as is
-    const int64_t r = INDEXED ? (int64_t)__ldg(h_index + v) : v;
-    const float4 a = ldg_f4(H + r * 200 + foff), b = ldg_f4(H + r * 200 + foff + 4);
-    acc[0] = a.x; acc[1] = a.y; acc[2] = a.z; acc[3] = a.w;
-    acc[4] = b.x; acc[5] = b.y; acc[6] = b.z; acc[7] = b.w;
-  }
-  const float nv = __ldg(norm + v);
-  float* op = Hout + (int64_t)v * 200 + foff;
-  float4 o0 = make_float4(acc[0] * nv, acc[1] * nv, acc[2] * nv, acc[3] * nv);
-  float4 o1 = make_float4(acc[4] * nv, acc[5] * nv, acc[6] * nv, acc[7] * nv);
-  if (HAS_LOOP) {
-    const float4 l0 = *reinterpret_cast<const float4*>(op), l1 = *reinterpret_cast<const float4*>(op + 4);
-    o0.x += l0.x; o0.y += l0.y; o0.z += l0.z; o0.w += l0.w;
-    o1.x += l1.x; o1.y += l1.y; o1.z += l1.z; o1.w += l1.w;
-  }
-  if (RELU) {
-    o0.x = fmaxf(o0.x, 0.f); o0.y = fmaxf(o0.y, 0.f); o0.z = fmaxf(o0.z, 0.f); o0.w = fmaxf(o0.w, 0.f);
-    o1.x = fmaxf(o1.x, 0.f); o1.y = fmaxf(o1.y, 0.f); o1.z = fmaxf(o1.z, 0.f); o1.w = fmaxf(o1.w, 0.f);
-  }
-  st_f4(op, o0);
-  st_f4(op + 4, o1);
 }
 
 // Generic shapes (any d_in, d_out, num_bases): one thread per (node, output feature).  Only the
@@ -137,8 +97,8 @@ int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, c
                     ((reinterpret_cast<uintptr_t>(H) | reinterpret_cast<uintptr_t>(W) |
                       reinterpret_cast<uintptr_t>(Hout)) & 15) == 0;
   if (fast) {
-    const unsigned grid = (unsigned)((N + kWarpsPerCta - 1) / kWarpsPerCta);
-    const unsigned block = kWarpsPerCta * 32;
+    const unsigned grid = (unsigned)((N + kTileNodes - 1) / kTileNodes);
+    const unsigned block = kTileWarps * 32;
 #define RENET_LAUNCH_GATHER(R, L, I)                                                                   \
   rgcn_gather_d200_kernel<R, L, I><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, \
                                                                norm, Hout, (int)N, passthrough)

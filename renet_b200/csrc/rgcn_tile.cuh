@@ -1,0 +1,136 @@
+// CTA-cooperative fused gather for the RE-Net shape (d_in = d_out = 200, 100 blocks of 2x2).
+//
+// One CTA owns kNodesPerCta consecutive destination rows of a CSR and the contiguous edge range that
+// feeds them.  The edge range is split EVENLY over the CTA's warps (degree skew -- ICEWS18 in-degrees:
+// median 3, p99 53, max 148 -- no longer idles warps); each warp walks its slice, keeps the running
+// destination's sum in registers (a warp-level segmented reduction: edges are destination-sorted) and
+// flushes it into a shared-memory tile when the destination changes.  The epilogue applies
+// norm / self-loop / activation from the tile with fully coalesced 8-byte accesses.
+//
+// Lane mapping (fully coalesced): lane l < 25 owns blocks {l, l+25, l+50, l+75}.  Per edge it issues
+// 4 x LDG.64 on the source row (each instruction covers 200 contiguous bytes across the warp,
+// L1::no_allocate: streamed) and 4 x LDG.128 on the relation's block table row (400 contiguous bytes
+// per instruction, L1-allocating: hot relations stay in L1).
+//
+// The same body serves forward (Hout = act(norm*agg + loop)) and backward-dH (reverse CSR, transposed
+// 2x2 blocks, per-edge scale norm[dst], no activation).
+#pragma once
+#include "common.cuh"
+
+namespace renet {
+
+constexpr int kTileNodes = 16;
+constexpr int kTileWarps = 8;
+
+__device__ __forceinline__ float2 ldg_f2_stream(const float* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+
+struct EdgeData {
+  float2 h[4];
+  float4 w[4];
+};
+
+__device__ __forceinline__ void load_edge(EdgeData& d, const float* __restrict__ X, const float* __restrict__ W,
+                                          int s, int t, int lane) {
+  const float* xp = X + (int64_t)s * 200 + 2 * lane;
+  const float* wp = W + (int64_t)t * 400 + 4 * lane;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    d.h[k] = ldg_f2_stream(xp + 50 * k);
+    d.w[k] = ldg_f4(wp + 100 * k);
+  }
+}
+
+template <bool TRANSPOSE>
+__device__ __forceinline__ void fma_edge(float (&acc)[8], const EdgeData& d, float sc) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float x = d.h[k].x * sc, y = d.h[k].y * sc;
+    const float4 w = d.w[k];   // block (w.x w.y; w.z w.w) = W[b][i][j] row-major
+    if (!TRANSPOSE) {          // out[j] += sum_i in[i] * W[i][j]
+      acc[2 * k] = fmaf(x, w.x, fmaf(y, w.z, acc[2 * k]));
+      acc[2 * k + 1] = fmaf(x, w.y, fmaf(y, w.w, acc[2 * k + 1]));
+    } else {                   // din[i] += sum_j W[i][j] * g[j]
+      acc[2 * k] = fmaf(x, w.x, fmaf(y, w.y, acc[2 * k]));
+      acc[2 * k + 1] = fmaf(x, w.z, fmaf(y, w.w, acc[2 * k + 1]));
+    }
+  }
+}
+
+// Accumulate the tile's messages into `agg` (shared, [kTileNodes][200], zeroed by this function).
+// s_rp: shared copy of row_ptr[v0 .. v0+nv].  EDGE_SCALE: multiply each message by scale[col_a[e]]
+// (backward: norm of the edge's destination).
+template <bool TRANSPOSE, bool INDEXED, bool EDGE_SCALE>
+__device__ __forceinline__ void tile_accumulate(float (*agg)[200], const int* s_rp, int nv,
+                                                const float* __restrict__ X, const int32_t* __restrict__ x_index,
+                                                const float* __restrict__ W, const int32_t* __restrict__ col_a,
+                                                const int32_t* __restrict__ col_type,
+                                                const float* __restrict__ scale) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool active = lane < 25;
+  const int ebeg = s_rp[0], eend = s_rp[nv];
+  const int chunk = (eend - ebeg + kTileWarps - 1) / kTileWarps;
+  const int e0 = ebeg + warp * chunk;
+  const int e1 = min(eend, e0 + chunk);
+  if (e0 >= e1) return;
+  int node = 0;
+  while (s_rp[node + 1] <= e0) ++node;
+  int node_end = s_rp[node + 1];
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+  auto flush = [&](int nd) {
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        atomicAdd(&agg[nd][2 * (lane + 25 * k)], acc[2 * k]);
+        atomicAdd(&agg[nd][2 * (lane + 25 * k) + 1], acc[2 * k + 1]);
+        acc[2 * k] = acc[2 * k + 1] = 0.f;
+      }
+    }
+  };
+  auto advance = [&](int e) {   // warp-uniform
+    if (e >= node_end) {
+      flush(node);
+      do { ++node; node_end = s_rp[node + 1]; } while (e >= node_end);
+    }
+  };
+
+  for (int base = e0; base < e1; base += 32) {
+    const int e = base + lane;
+    int my_s = 0, my_t = 0;
+    float my_sc = 1.f;
+    if (e < e1) {
+      my_s = __ldg(col_a + e);
+      my_t = __ldg(col_type + e);
+      if (EDGE_SCALE) my_sc = __ldg(scale + my_s);
+      if (INDEXED) my_s = __ldg(x_index + my_s);
+    }
+    const int cnt = min(32, e1 - base);
+    for (int j = 0; j < cnt; j += 2) {
+      const int sa = __shfl_sync(0xffffffffu, my_s, j), ta = __shfl_sync(0xffffffffu, my_t, j);
+      const int jb = min(j + 1, cnt - 1);
+      const int sb = __shfl_sync(0xffffffffu, my_s, jb), tb = __shfl_sync(0xffffffffu, my_t, jb);
+      const float ca = EDGE_SCALE ? __shfl_sync(0xffffffffu, my_sc, j) : 1.f;
+      const float cb = EDGE_SCALE ? __shfl_sync(0xffffffffu, my_sc, jb) : 1.f;
+      EdgeData da, db;
+      if (active) {             // both edges' 16 loads are issued before any use
+        load_edge(da, X, W, sa, ta, lane);
+        load_edge(db, X, W, sb, tb, lane);
+      }
+      advance(base + j);
+      if (active) fma_edge<TRANSPOSE>(acc, da, ca);
+      if (j + 1 < cnt) {
+        advance(base + j + 1);
+        if (active) fma_edge<TRANSPOSE>(acc, db, cb);
+      }
+    }
+  }
+  flush(node);
+}
+
+}  // namespace renet
