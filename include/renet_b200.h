@@ -40,6 +40,13 @@ const char* renet_last_error(void);
  * "gpu_launches" claim). */
 int64_t renet_launch_count(void);
 
+/* Dense-GEMM engine used for the self-loop and GRU projections: 0 = FFMA (fp32 CUDA cores),
+ * 1 = tcgen05 3xTF32 (tensor cores, fp32-accurate split).  Both are this library's own kernels.
+ * Process-wide; the initial value comes from the RENET_GEMM environment variable (ffma|umma).
+ * renet_set_gemm_engine returns the previous engine. */
+int renet_set_gemm_engine(int engine);
+int renet_get_gemm_engine(void);
+
 /* ------------------------------------------------------------------------------------------------
  * Graph preprocessing.  Replaces what DGL does inside g.update_all (RGCN.py:91) to find the
  * in-edges of every node: turns the COO edge list of the batched history graph (dgl.batch,

@@ -54,6 +54,9 @@ int launch_pack_inputs(const float* H2, const int32_t* readout, const int32_t* r
                        const int32_t* seq_r, const int32_t* packed_row, float* X4, float* X3, int64_t S, int h,
                        cudaStream_t stream);
 
+int gemm_mode();
+int set_gemm_mode(int m);
+
 namespace {
 
 __global__ void iota_kernel(int32_t* p, int64_t n) {
@@ -96,6 +99,8 @@ extern "C" {
 int renet_version(void) { return 100; /* 0.1.0 */ }
 const char* renet_last_error(void) { return g_err; }
 int64_t renet_launch_count(void) { return g_launches.load(); }
+int renet_set_gemm_engine(int engine) { return set_gemm_mode(engine); }
+int renet_get_gemm_engine(void) { return gemm_mode(); }
 
 int64_t renet_csr_workspace_bytes(int64_t N, int64_t E) {
   size_t cub_bytes = 0;

@@ -4,6 +4,9 @@
 //
 // Tile: 80 x 200 outputs per CTA (d_out = 200, 600 and 1200 are all multiples of 200, so no column
 // waste), 8x8 outputs per thread, K stepped by 8 with register-staged double buffering.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace renet {
@@ -232,10 +235,33 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 }  // namespace
 
+int umma_gemm_nn_try(const float* A, const int32_t* a_index, int64_t lda, const float* B, int64_t ldb, float* C,
+                     int64_t ldc, const float* bias, int64_t M, int32_t N, int32_t K, bool accumulate,
+                     cudaStream_t stream);
+
+// RENET_GEMM=ffma|umma selects the dense-GEMM engine (both are this library's own sm_100a kernels).
+static int g_gemm_mode = -1;
+int gemm_mode() {
+  if (g_gemm_mode < 0) {
+    const char* e = getenv("RENET_GEMM");
+    g_gemm_mode = (e != nullptr && strcmp(e, "umma") == 0) ? 1 : 0;
+  }
+  return g_gemm_mode;
+}
+int set_gemm_mode(int m) {
+  const int prev = gemm_mode();
+  g_gemm_mode = m ? 1 : 0;
+  return prev;
+}
+
 int sgemm_nn(const float* A, const int32_t* a_index, int64_t lda, const float* B, int64_t ldb, float* C,
              int64_t ldc, const float* bias, int64_t M, int32_t N, int32_t K, bool accumulate,
              cudaStream_t stream) {
   if (M <= 0 || N <= 0) return RENET_OK;
+  if (gemm_mode() == 1) {   // tcgen05 3xTF32 path (umma_gemm.cu); returns 0 when the shape is not supported
+    const int r = umma_gemm_nn_try(A, a_index, lda, B, ldb, C, ldc, bias, M, N, K, accumulate, stream);
+    if (r != 0) return r < 0 ? r : RENET_OK;
+  }
   const bool fast = (K % 4 == 0) && (N % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) &&
                     aligned16(A) && aligned16(B) && aligned16(C) && (bias == nullptr || aligned16(bias));
   if (fast) {

@@ -1,0 +1,308 @@
+// fp32-accurate GEMM on the 5th-generation tensor cores: C[M,N] = A[M,K] @ B[K,N] (+bias) (+C)
+//
+// RE-Net's dense work on the hot path -- the self-loop H @ W_loop (RGCN.py:35) and the GRU input /
+// recurrent projections (model.py:86,94) -- must match a CPU fp32 oracle to 1e-4, which single-pass
+// TF32 (10-bit mantissa, ~3e-4 on K=200) does not.  This kernel issues tcgen05.mma kind::tf32 with the
+// 3xTF32 split:  a = a_hi + a_lo,  b = b_hi + b_lo  (hi = top 19 bits, lo = a - a_hi exactly),
+//     D += a_hi*b_hi + a_lo*b_hi + a_hi*b_lo        (fp32 accumulation in TMEM)
+// which recovers ~fp32 accuracy (dropped term a_lo*b_lo ~ 2^-22 relative) at 1/3 of TF32 peak -- still
+// several times the FFMA roofline.
+//
+// Structure (one CTA per 128-row tile of A x one <=200-column tile of B, 256 threads):
+//   * operands are staged by the threads themselves (not TMA): A rows may be gathered through an index
+//     (fused embedding lookup / read-out), B is row-major [K,N] and has to be transposed to K-major,
+//     and both need the hi/lo split, so a register pass is required anyway;
+//   * smem holds two stages of {A_hi, A_lo [128 x 40], B_hi, B_lo [208 x 40]} in the canonical
+//     no-swizzle K-major UMMA layout (8-row x 16-byte core matrices; LBO = one 4-column slab,
+//     SBO = 128 B);
+//   * one elected thread issues 15 MMAs (5 k-steps x 3 split products, M=128, N=208, K=8) per stage and
+//     commits to an mbarrier that frees the stage; loads of chunk c+1 overlap the MMAs of chunk c;
+//   * accumulator: 128 lanes x 208 fp32 columns of TMEM (256 allocated); epilogue reads it with
+//     tcgen05.ld 32x32b (thread = row) and writes C with bias / accumulate applied.
+#include "common.cuh"
+
+namespace renet {
+namespace {
+
+constexpr int UM = 128;          // rows per CTA tile
+constexpr int UN = 200;          // logical columns per CTA tile
+constexpr int UNP = 208;         // padded to a multiple of 16 for the MMA N
+constexpr int UKC = 40;          // K per stage (5 MMA k-steps of 8)
+constexpr int USLABS = UKC / 4;  // 16-byte (4 x fp32) column slabs per stage
+constexpr int UTHREADS = 256;
+constexpr int A_SLAB_BYTES = UM * 16;    // 2048
+constexpr int B_SLAB_BYTES = UNP * 16;   // 3328
+constexpr int A_BYTES = USLABS * A_SLAB_BYTES;   // 20480
+constexpr int B_BYTES = USLABS * B_SLAB_BYTES;   // 33280
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 107520
+constexpr int NUM_STAGES = 2;
+constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 64;   // + mbarriers / tmem pointer
+constexpr int TMEM_COLS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+// Bounded spin: a wrong descriptor must fail the launch (trap), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (int spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spins > (1 << 20)) __trap();
+  }
+}
+
+// K-major, no swizzle: LBO = byte distance between the two 16-byte K-slabs of one MMA, SBO = byte
+// distance between consecutive 8-row core matrices; version = 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// kind::tf32, fp32 accumulate, A and B K-major, M=128, N=208
+__device__ __forceinline__ uint32_t make_idesc() {
+  uint32_t d = 0;
+  d |= 1u << 4;                 // c_format = F32
+  d |= 2u << 7;                 // a_format = TF32
+  d |= 2u << 10;                // b_format = TF32
+  d |= (uint32_t)(UNP >> 3) << 17;
+  d |= (uint32_t)(UM >> 4) << 24;
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  lo = v - hi;
+}
+__device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
+  split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
+  split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+}
+
+template <bool INDEXED>
+__global__ void __launch_bounds__(UTHREADS, 1)
+umma_gemm_nn_kernel(const float* __restrict__ A, const int32_t* __restrict__ a_index, int64_t lda,
+                    const float* __restrict__ B, int64_t ldb, float* __restrict__ C, int64_t ldc,
+                    const float* __restrict__ bias, int64_t M, int N, int K, int accumulate) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * UM;
+  const int n0 = blockIdx.y * UN;
+  const int tile_n = min(UN, N - n0);
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NUM_STAGES * STAGE_BYTES);   // [0..1] stage free, [2] done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + NUM_STAGES * STAGE_BYTES + 32);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar0 = smem_u32(bars);
+
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    mbar_init(bar0 + 16, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // zero the 8 padding rows (n = 200..207) of every B slab once; they are never written again
+  for (int i = tid; i < NUM_STAGES * 2 * USLABS * (UNP - UN); i += UTHREADS) {
+    const int r = i % (UNP - UN), sl = (i / (UNP - UN)) % USLABS, which = (i / ((UNP - UN) * USLABS)) % 2,
+              st = i / ((UNP - UN) * USLABS * 2);
+    float4* p = reinterpret_cast<float4*>(smem + st * STAGE_BYTES + 2 * A_BYTES + which * B_BYTES + sl * B_SLAB_BYTES +
+                                          (UN + r) * 16);
+    *p = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = make_idesc();
+
+  // per-thread A source rows: task = slab * 128 + row  (5 tasks per thread per chunk)
+  const float* a_rows[5];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) {
+    const int task = tid + t * UTHREADS;
+    const int r = task % UM;
+    const int64_t gr = row0 + r;
+    a_rows[t] = nullptr;
+    if (gr < M) {
+      const int64_t rr = INDEXED ? (int64_t)__ldg(a_index + gr) : gr;
+      a_rows[t] = A + rr * lda;
+    }
+  }
+
+  const int nchunks = K / UKC;
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c % NUM_STAGES;
+    uint8_t* sA_hi = smem + st * STAGE_BYTES;
+    uint8_t* sA_lo = sA_hi + A_BYTES;
+    uint8_t* sB_hi = sA_lo + A_BYTES;
+    uint8_t* sB_lo = sB_hi + B_BYTES;
+    if (c >= NUM_STAGES) mbar_wait(bar0 + 8 * st, ((c / NUM_STAGES) - 1) & 1);   // MMAs of chunk c-2 done
+    const int k0 = c * UKC;
+    // ---- A: 128 rows x 10 slabs; thread -> (slab, row): conflict-free 16-byte smem stores ----------
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+      const int task = tid + t * UTHREADS;
+      const int sl = task / UM, r = task % UM;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a_rows[t] != nullptr) v = ldg_f4(a_rows[t] + k0 + 4 * sl);
+      float4 hi, lo;
+      split4(v, hi, lo);
+      *reinterpret_cast<float4*>(sA_hi + sl * A_SLAB_BYTES + r * 16) = hi;
+      *reinterpret_cast<float4*>(sA_lo + sl * A_SLAB_BYTES + r * 16) = lo;
+    }
+    // ---- B: [40 k] x [200 n] row-major -> K-major: 4x4 register transposes -----------------------------
+    for (int task = tid; task < USLABS * (UN / 4); task += UTHREADS) {
+      const int sl = task / (UN / 4), j = task % (UN / 4);
+      float4 m[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        m[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (4 * j < tile_n) m[i] = ldg_f4(B + (int64_t)(k0 + 4 * sl + i) * ldb + n0 + 4 * j);
+      }
+      const float4 t0 = make_float4(m[0].x, m[1].x, m[2].x, m[3].x);
+      const float4 t1 = make_float4(m[0].y, m[1].y, m[2].y, m[3].y);
+      const float4 t2 = make_float4(m[0].z, m[1].z, m[2].z, m[3].z);
+      const float4 t3 = make_float4(m[0].w, m[1].w, m[2].w, m[3].w);
+      const float4 tr[4] = {t0, t1, t2, t3};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 hi, lo;
+        split4(tr[q], hi, lo);
+        *reinterpret_cast<float4*>(sB_hi + sl * B_SLAB_BYTES + (4 * j + q) * 16) = hi;
+        *reinterpret_cast<float4*>(sB_lo + sl * B_SLAB_BYTES + (4 * j + q) * 16) = lo;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (MMA)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = smem_base + st * STAGE_BYTES, a_lo = a_hi + A_BYTES;
+      const uint32_t b_hi = a_lo + A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+      for (int ks = 0; ks < UKC / 8; ++ks) {
+        const uint32_t ao = ks * 2 * A_SLAB_BYTES, bo = ks * 2 * B_SLAB_BYTES;
+        const uint64_t dAh = make_desc(a_hi + ao, A_SLAB_BYTES, 128), dAl = make_desc(a_lo + ao, A_SLAB_BYTES, 128);
+        const uint64_t dBh = make_desc(b_hi + bo, B_SLAB_BYTES, 128), dBl = make_desc(b_lo + bo, B_SLAB_BYTES, 128);
+        umma_tf32(tmem_base, dAh, dBh, idesc, (c | ks) != 0);
+        umma_tf32(tmem_base, dAl, dBh, idesc, 1);
+        umma_tf32(tmem_base, dAh, dBl, idesc, 1);
+      }
+      umma_commit(bar0 + 8 * st);                         // frees this stage when the MMAs have read it
+      if (c == nchunks - 1) umma_commit(bar0 + 16);       // accumulator complete
+    }
+  }
+
+  // ---- epilogue: TMEM -> registers -> global (thread = row; warps 0-3 cols [0,104), warps 4-7 [104,208)) ---
+  mbar_wait(bar0 + 16, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane;
+    const int64_t gr = row0 + r;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int cc = half * 104; cc < half * 104 + 104; cc += 8) {
+      uint32_t v[8];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                   : "r"(taddr + (uint32_t)cc));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (gr < M && cc < tile_n) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[i]);
+        float* cp = C + gr * ldc + n0 + cc;
+        if (bias != nullptr) {
+          const float4 b0 = ldg_f4(bias + n0 + cc), b1 = ldg_f4(bias + n0 + cc + 4);
+          o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+          o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+        }
+        if (accumulate) {
+          const float4 c0 = *reinterpret_cast<const float4*>(cp), c1 = *reinterpret_cast<const float4*>(cp + 4);
+          o[0] += c0.x; o[1] += c0.y; o[2] += c0.z; o[3] += c0.w;
+          o[4] += c1.x; o[5] += c1.y; o[6] += c1.z; o[7] += c1.w;
+        }
+        st_f4(cp, make_float4(o[0], o[1], o[2], o[3]));
+        st_f4(cp + 4, make_float4(o[4], o[5], o[6], o[7]));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace
+
+// Returns 1 if the shape was taken by the tensor-core path (launch enqueued), 0 if the caller should
+// fall back to the FFMA kernel, negative on error.
+int umma_gemm_nn_try(const float* A, const int32_t* a_index, int64_t lda, const float* B, int64_t ldb, float* C,
+                     int64_t ldc, const float* bias, int64_t M, int32_t N, int32_t K, bool accumulate,
+                     cudaStream_t stream) {
+  const bool ok = (K % UKC == 0) && K >= UKC && (N % 8 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) &&
+                  M >= 64 &&
+                  ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C) |
+                    reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
+  if (!ok) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(umma_gemm_nn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e2 = cudaFuncSetAttribute(umma_gemm_nn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(umma_gemm_nn_kernel) failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      return RENET_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((M + UM - 1) / UM), (unsigned)((N + UN - 1) / UN));
+  if (a_index)
+    umma_gemm_nn_kernel<true><<<grid, UTHREADS, SMEM_BYTES, stream>>>(A, a_index, lda, B, ldb, C, ldc, bias, M, N, K, accumulate);
+  else
+    umma_gemm_nn_kernel<false><<<grid, UTHREADS, SMEM_BYTES, stream>>>(A, a_index, lda, B, ldb, C, ldc, bias, M, N, K, accumulate);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("launch of umma_gemm_nn_kernel failed: %s", cudaGetErrorString(e));
+    return RENET_ERR_CUDA;
+  }
+  count_launch();
+  return 1;
+}
+
+}  // namespace renet

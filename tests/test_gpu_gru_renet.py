@@ -83,6 +83,29 @@ def test_training_path_gradients_match_reference_golden():
                 assert rel_err(p.grad.cpu().numpy(), b[key]) < 5 * TOL, (tag, k)
 
 
+@pytest.mark.parametrize('fname', ['renet_tiny.npz', 'renet_icews18_slice.npz'])
+def test_fused_training_step_gradients_match_reference_golden(fname):
+    """RENet.forward (fused RGCN + fused GRU, dropout 0) -> loss.backward() entirely through the CUDA
+    kernels (renet_rgcn_block_bwd, renet_gru_bwd) vs the reference's autograd gradients."""
+    b, m, params, glob, gd, batch, sh, oh, quads, sel, dims = _setup(fname)
+    m.train()
+    for tag, subj in (('subj', True), ('obj', False)):
+        m.zero_grad()
+        loss = m(batch, sh, oh, gd, subject=subj)
+        loss.backward()
+        assert abs(loss.item() - float(b[tag + '/loss'])) < TOL * abs(float(b[tag + '/loss']))
+        for k, p in m.named_parameters():
+            if (tag + '/grad/' + k) in b.files:
+                assert rel_err(p.grad.cpu().numpy(), b[tag + '/grad/' + k]) < 5 * TOL, (tag, k)
+            else:
+                g = p.grad.double().cpu()
+                scale = float(b['%s/grad_norm/%s' % (tag, k)])
+                assert abs(g.norm().item() - scale) < 5 * TOL * scale, (tag, k)
+                for ax, nm in ((1, 'grad_rowsum'), (0, 'grad_colsum')):
+                    diff = np.abs(g.sum(ax).numpy() - b['%s/%s/%s' % (tag, nm, k)]).max()
+                    assert diff < 50 * TOL * scale, (tag, k, nm)
+
+
 def test_fused_gru_vs_oracle_synthetic():
     """renet_gru_fwd on an ICEWS18-shaped batch (h=200) against the CPU oracle's explicit recurrence."""
     from renet_b200 import synthetic, utils

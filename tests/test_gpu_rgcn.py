@@ -176,6 +176,6 @@ def test_full_size_properties(G):
     rp2, cs2, ct2 = G.csr_from_coo(src[perm], dst[perm], et[perm], N)
     c = G.layer_fwd(H, None, W, Wl, rp2, cs2, ct2, norm, N, E, 200, 200, 100, False)
     assert rel_err(c.cpu().numpy(), a.cpu().numpy()) < 1e-5
-    # relu idempotence: relu(layer) >= 0 and equals max(layer, 0)
+    # relu(layer) == max(layer, 0) (up to the summation order of partial sums of split destinations)
     r = G.layer_fwd(H, None, W, Wl, rp, cs, ct, norm, N, E, 200, 200, 100, True)
-    assert torch.equal(r, torch.clamp_min(a, 0))
+    assert float((r - torch.clamp_min(a, 0)).abs().max()) < 1e-5 and float(r.min()) >= 0.0
