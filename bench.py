@@ -58,50 +58,60 @@ def algorithmic_bytes(N, E, R2):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is
+    polled in-process every few ms (a fresh `nvidia-smi -lms` takes longer to start than the timed region
+    lasts); falls back to one nvidia-smi query if pynvml is unavailable."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self.t = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = int(vis.split(',')[self.index]) if vis and vis.split(',')[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {'hw_slowdown': getattr(pynvml, 'nvmlClocksEventReasonHwSlowdown', 0x8),
+                    'hw_thermal_slowdown': getattr(pynvml, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+                    'sw_thermal_slowdown': getattr(pynvml, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
+                    'sw_power_cap': getattr(pynvml, 'nvmlClocksEventReasonSwPowerCap', 0x4)}
+
+            def poll():
+                get_reasons = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons',
+                                      getattr(pynvml, 'nvmlDeviceGetCurrentClocksThrottleReasons', None))
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        if get_reasons is not None:
+                            r = int(get_reasons(h))
+                            for n, b in bits.items():
+                                if r & b:
+                                    self.reasons.add(n)
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.t = threading.Thread(target=poll, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.t = None
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.t is not None:
+            self._stop.set()
+            self.t.join(timeout=1)
+            return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.max_mhz,
+                    'samples': len(self.sm), 'reasons': sorted(self.reasons), 'source': 'nvml, polled every 2 ms'}
         try:
-            self.proc.wait(timeout=2)
+            out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=clocks.sm,clocks.max.sm',
+                                  '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=10).stdout
+            f = [float(x) for x in out.strip().split(',')]
+            return {'sm_mhz': f[0], 'sm_max_mhz': f[1], 'samples': 1, 'reasons': [], 'source': 'nvidia-smi after the run'}
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
-            f = [x.strip() for x in r.split(',')]
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except Exception:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(n)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'samples': 0, 'reasons': ['clock query unavailable']}
 
 
 def measured_peak_gbs():

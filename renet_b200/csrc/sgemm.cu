@@ -244,7 +244,7 @@ static int g_gemm_mode = -1;
 int gemm_mode() {
   if (g_gemm_mode < 0) {
     const char* e = getenv("RENET_GEMM");
-    g_gemm_mode = (e != nullptr && strcmp(e, "umma") == 0) ? 1 : 0;
+    g_gemm_mode = (e != nullptr && strcmp(e, "ffma") == 0) ? 0 : 1;   // default: tensor cores
   }
   return g_gemm_mode;
 }
