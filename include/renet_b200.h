@@ -191,6 +191,36 @@ int renet_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_gl
                   const void* fwd_workspace, void* bwd_workspace, int64_t bwd_workspace_bytes,
                   void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * HOST-side batching of history graphs (no CUDA; every pointer here is a HOST pointer).  Replaces
+ * utils.get_sorted_s_r_embed_rgcn / get_s_r_embed_rgcn minus the embedding lookups (utils.py:209-283):
+ * get_neighs_by_t :149-156, get_g_list_id + make_subgraph :158-170,115-131, get_node_ids_to_g_id
+ * :172-181, dgl.batch :238, and the pack_padded_sequence bookkeeping of Aggregator.py:160-165.
+ *
+ * Graph store (built once from graph_dict): graph g owns nodes g_node_off[g]..g_node_off[g+1]
+ * (g_node_ent ascending) and edges g_edge_off[g].. (LOCAL rows g_src/g_dst, sorted by g_dst, with
+ * g_type_s / g_type_o).  History store (built once from the s_hist / s_hist_t lists): sample i owns
+ * the entry ids h_samp_entry[h_samp_off[i] .. h_samp_off[i+1]) (entries are shared between samples, as
+ * the reference's lists share arrays); entry e happened in graph h_ent_graph[e], its subject sits at
+ * local row h_ent_srow[e], its neighbours at local rows h_nbr_row[h_ent_off[e] .. h_ent_off[e+1]).
+ *
+ * Output: s_idx_out [B] (sample order: history length descending, stable, when sort != 0), the batched
+ * graph in CSR form + bookkeeping packed into `out` (int32 words, one H2D copy):
+ *   node_ent[N] row_ptr[N+1] col_src[E] col_type_s[E] col_type_o[E] norm[N](float bits)
+ *   readout[S] row_comp[S] row_seq[S] seq_start[Q] seq_len[Q] packed_row[S]
+ * comp_graph_out [G] (graph index of every component, first-appearance order), batch_sizes_out
+ * [max_len], sizes = {N, E, S, Q, G, max_len, words_used, 0}.
+ * Returns 0, or 1 when out_capacity < words_used (sizes is filled: grow and call again), <0 on error.
+ * ---------------------------------------------------------------------------------------------- */
+int renet_host_assemble_batch(
+    int64_t T, const int64_t* g_node_off, const int32_t* g_node_ent, const int64_t* g_edge_off,
+    const int32_t* g_src, const int32_t* g_dst, const int32_t* g_type_s, const int32_t* g_type_o,
+    const int64_t* h_samp_off, const int64_t* h_samp_entry, const int32_t* h_ent_graph, const int32_t* h_ent_srow,
+    const int64_t* h_ent_off, const int32_t* h_nbr_row,
+    const int64_t* sample_idx, int64_t B, int32_t sort,
+    int64_t* s_idx_out, int32_t* out, int64_t out_capacity, int32_t* comp_graph_out,
+    int32_t* batch_sizes_out, int32_t max_len_capacity, int64_t* sizes);
+
 /* Materialise the packed GRU inputs exactly as the reference's aggregator returns them
  * (PackedSequence.data, time-major: Aggregator.py:160-165):  X4 [S,4h], X3 [S,3h];
  * packed_row [S] maps packed position -> sequence-major row. */

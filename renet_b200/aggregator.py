@@ -68,6 +68,12 @@ class RGCNAggregator(nn.Module):
 
     # ---------------------------------------------------------------------------------------------
     def _batch(self, s_hist, s, graph_dict, device, sort):
+        from .hoststore import HistoryView, assemble_view
+        if isinstance(s_hist, HistoryView):          # flat stores + C++ batcher (renet_host_assemble_batch)
+            if s_hist.total_length() == 0:
+                raise ValueError('RGCNAggregator: every history in the batch is empty '
+                                 '(the reference fails on this input too, Aggregator.py:128-129,167)')
+            return assemble_view(s_hist, device, sort)
         total = 0
         for his in s_hist[0]:
             total += len(his)

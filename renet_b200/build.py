@@ -19,7 +19,7 @@ FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std
 
 
 def sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cu'))
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cpp')))
 
 
 def _digest():
@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     for src in sources():
-        obj = os.path.join(BUILD_DIR, os.path.basename(src)[:-3] + '.o')
+        obj = os.path.join(BUILD_DIR, os.path.splitext(os.path.basename(src))[0] + '.o')
         cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

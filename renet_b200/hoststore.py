@@ -1,0 +1,219 @@
+"""Flat host-side stores + the C++ batcher (renet_host_assemble_batch): the fast path of
+reference utils.get_sorted_s_r_embed_rgcn (utils.py:209-244).
+
+The reference hands `RENet.forward` Python lists (`s_hist`: list[B] of list[<=10] of int arrays [k,2]) and a
+dict of per-timestamp graphs, and re-walks them in Python for every batch.  Here both are flattened ONCE:
+
+    gs = GraphStore(graph_dict)                       # all timestamps' graphs, CSR-ready
+    hs = HistoryStore(s_hist_all, s_hist_t_all, subjects_all, gs)   # the training set's histories
+    view = hs.select(sample_indices)                  # what a batch is: just indices
+
+and ``model(triplets, view_s, view_o, gs, subject=...)`` assembles the batched history graph in C++ in a few
+milliseconds, writes it into a pinned staging buffer and ships it to the GPU in one copy.  The list-based
+API keeps working (numpy path in utils.py); both produce identical batches (tests/test_host_batching.py).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .graph import BatchedHistoryGraph, _Frame, as_history_graph
+from .utils import HistoryBatch
+
+MAX_LEN = 16
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class GraphStore:
+    """All per-timestamp graphs of a graph_dict, concatenated (nodes ascending by entity id, edges sorted by
+    destination).  Quacks like the dict for the rest of the code (``store[t]``, ``in``, ``keys()``)."""
+
+    def __init__(self, graph_dict):
+        self.graph_dict = graph_dict
+        self.times = np.asarray(sorted(int(t) for t in graph_dict.keys()), dtype=np.int64)
+        self.index_of = {int(t): i for i, t in enumerate(self.times)}
+        graphs = [as_history_graph(graph_dict[int(t)]) for t in self.times]
+        for g in graphs:
+            if not g._sorted:
+                raise ValueError('GraphStore needs graphs whose node ids ascend (utils.get_big_graph order)')
+        self.node_off = np.concatenate(([0], np.cumsum([g.number_of_nodes() for g in graphs]))).astype(np.int64)
+        self.edge_off = np.concatenate(([0], np.cumsum([g.number_of_edges() for g in graphs]))).astype(np.int64)
+        cat = lambda xs, dt: np.ascontiguousarray(np.concatenate(xs), dtype=dt) if xs else np.zeros(0, dt)
+        self.node_ent = cat([g.node_id for g in graphs], np.int32)
+        self.src = cat([g.src for g in graphs], np.int32)
+        self.dst = cat([g.dst for g in graphs], np.int32)
+        self.type_s = cat([g.type_s for g in graphs], np.int32)
+        self.type_o = cat([g.type_o for g in graphs], np.int32)
+        self.graphs = graphs
+
+    def __getitem__(self, t):
+        return self.graph_dict[t]
+
+    def __contains__(self, t):
+        return t in self.graph_dict
+
+    def keys(self):
+        return self.graph_dict.keys()
+
+    def local_rows(self, gi, entities):
+        lo = self.node_off[gi]
+        ent = self.node_ent[lo:self.node_off[gi + 1]]
+        rows = np.searchsorted(ent, entities)
+        if np.any(rows >= len(ent)) or np.any(ent[np.minimum(rows, len(ent) - 1)] != entities):
+            raise KeyError('entity not present in the graph of timestamp %d' % int(self.times[gi]))
+        return rows.astype(np.int32)
+
+
+class HistoryStore:
+    """Histories of a whole split (the reference's pickled train_history_{sub,ob}.txt), flattened, with every
+    entity already resolved to its local row in that timestamp's graph."""
+
+    def __init__(self, hist, hist_t, subjects, graph_store):
+        self.gs = graph_store
+        n = len(hist)
+        self.subjects = np.asarray(subjects, dtype=np.int64)
+        lens = np.fromiter((len(h) for h in hist), dtype=np.int64, count=n)
+        self.samp_off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+        samp_entry = np.empty(int(self.samp_off[-1]), dtype=np.int64)
+        ent_graph, ent_srow, nbr_rows = [], [], []
+        k = 0
+        cache = {}       # the reference's lists share one array per (entity, timestamp): key on identity
+        for i in range(n):
+            s = int(self.subjects[i])
+            for neighs, t in zip(hist[i], hist_t[i]):
+                key = (id(neighs), s)
+                e = cache.get(key)
+                if e is None:
+                    gi = graph_store.index_of[int(t)]
+                    e = cache[key] = len(ent_graph)
+                    ent_graph.append(gi)
+                    ent_srow.append(int(graph_store.local_rows(gi, np.asarray([s]))[0]))
+                    nbr_rows.append(graph_store.local_rows(gi, np.asarray(neighs)[:, 1]))
+                samp_entry[k] = e
+                k += 1
+        self.samp_entry = samp_entry
+        self.ent_graph = np.asarray(ent_graph, dtype=np.int32)
+        self.ent_srow = np.asarray(ent_srow, dtype=np.int32)
+        self.ent_off = np.concatenate(([0], np.cumsum([len(x) for x in nbr_rows]))).astype(np.int64)
+        self.nbr_row = np.ascontiguousarray(np.concatenate(nbr_rows), dtype=np.int32) if nbr_rows else np.zeros(0, np.int32)
+        self._keepalive = hist        # the id()-keyed cache relies on the arrays staying alive during __init__
+
+    def select(self, sample_idx):
+        return HistoryView(self, np.ascontiguousarray(sample_idx, dtype=np.int64))
+
+
+class HistoryView:
+    """A batch = indices into a HistoryStore.  Passed where the reference passes (s_hist, s_hist_t)."""
+
+    def __init__(self, store, sample_idx):
+        self.store, self.sample_idx = store, sample_idx
+
+    def __len__(self):
+        return len(self.sample_idx)
+
+    def total_length(self):
+        so = self.store.samp_off
+        return int((so[self.sample_idx + 1] - so[self.sample_idx]).sum())
+
+
+class _Staging:
+    """Ring of pinned int32 staging buffers; a buffer is reused only after the H2D copy issued from it has
+    completed (event)."""
+
+    def __init__(self, n=3, words=1 << 21):
+        self.bufs = [torch.empty(words, dtype=torch.int32).pin_memory() for _ in range(n)]
+        self.events = [None] * n
+        self.i = 0
+
+    def next(self, min_words=0):
+        self.i = (self.i + 1) % len(self.bufs)
+        ev = self.events[self.i]
+        if ev is not None:
+            ev.synchronize()
+        if self.bufs[self.i].numel() < min_words:
+            self.bufs[self.i] = torch.empty(int(min_words * 1.5), dtype=torch.int32).pin_memory()
+        return self.i, self.bufs[self.i]
+
+
+_staging = {}
+
+
+def assemble_view_raw(view, out, sort=True):
+    """Run the C++ batcher into the int32 numpy buffer ``out`` (host only, no CUDA).  Returns None when
+    the buffer is too small (sizes[6] words are needed), else a dict of sizes + small host arrays."""
+    L = _lib.lib()
+    hs, gs = view.store, view.store.gs
+    B = len(view.sample_idx)
+    s_idx = np.empty(B, dtype=np.int64)
+    comp_graph = np.empty(len(gs.times), dtype=np.int32)
+    bsz = np.zeros(MAX_LEN, dtype=np.int32)
+    sizes = np.zeros(8, dtype=np.int64)
+    rc = L.renet_host_assemble_batch(
+        len(gs.times), _p(gs.node_off), _p(gs.node_ent), _p(gs.edge_off), _p(gs.src), _p(gs.dst), _p(gs.type_s),
+        _p(gs.type_o), _p(hs.samp_off), _p(hs.samp_entry), _p(hs.ent_graph), _p(hs.ent_srow), _p(hs.ent_off), _p(hs.nbr_row),
+        _p(view.sample_idx), B, int(sort), _p(s_idx), _p(out), out.size, _p(comp_graph), _p(bsz), MAX_LEN, _p(sizes))
+    if rc == 1:
+        return {'need_words': int(sizes[6])}
+    _lib.check(rc, 'renet_host_assemble_batch')
+    N, E, S, Q, G, max_len, words = (int(x) for x in sizes[:7])
+    return dict(N=N, E=E, S=S, Q=Q, G=G, max_len=max_len, words=words, s_idx=s_idx, comp_graph=comp_graph[:G],
+                batch_sizes=bsz[:max_len].copy())
+
+
+def split_raw(buf, r):
+    """Views into the staged buffer (numpy or torch), in the layout renet_host_assemble_batch documents."""
+    N, E, S, Q = r['N'], r['E'], r['S'], r['Q']
+    o = 0
+    out = {}
+    for name, n in (('node_ent', N), ('row_ptr', N + 1), ('col_src', E), ('col_type_s', E), ('col_type_o', E),
+                    ('norm', N), ('readout', S), ('row_comp', S), ('row_seq', S), ('seq_start', Q), ('seq_len', Q),
+                    ('packed_row', S)):
+        out[name] = buf[o:o + n]
+        o += n
+    return out
+
+
+def assemble_view(view, device, sort=True):
+    """HistoryView -> HistoryBatch on ``device`` through the C++ batcher (one pinned H2D copy)."""
+    st = _staging.setdefault(str(device), _Staging())
+    slot, buf = st.next()
+    r = assemble_view_raw(view, buf.numpy(), sort)
+    if 'need_words' in r:
+        st.bufs[slot] = buf = torch.empty(int(r['need_words'] * 1.5), dtype=torch.int32).pin_memory()
+        r = assemble_view_raw(view, buf.numpy(), sort)
+    hb = HistoryBatch()
+    hb.s_idx, hb.num_seq, hb.S = r['s_idx'], r['Q'], r['S']
+    if r['S'] == 0:
+        hb.graph, hb.seq_len = None, np.zeros(0, np.int64)
+        return hb
+    words = r['words']
+    dev = buf[:words].to(device, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    st.events[slot] = ev
+    d = split_raw(dev, r)
+    h = split_raw(buf.numpy(), r)
+    g = BatchedHistoryGraph.__new__(BatchedHistoryGraph)
+    g.device, g.N, g.E = torch.device(device), r['N'], r['E']
+    g.node_ent, g.row_ptr = d['node_ent'], d['row_ptr']
+    g.col_src, g.col_type_s, g.col_type_o = d['col_src'], d['col_type_s'], d['col_type_o']
+    g.norm = d['norm'].view(torch.float32)
+    g.comp_sizes = None
+    g.h2d_bytes = words * 4
+    g.ndata = _Frame(norm=g.norm.view(-1, 1), id=g.node_ent.view(-1, 1))
+    g.h_index = g.h_table = None
+    g._bwd = {}
+    g.seq_len_dev = d['seq_len']
+    hb.graph = g
+    hb.readout, hb.row_glob, hb.row_seq = d['readout'], d['row_comp'], d['row_seq']
+    hb.seq_start, hb.packed_row = d['seq_start'], d['packed_row']
+    hb.readout_host = h['readout'].astype(np.int64)
+    hb.seq_len = h['seq_len'].astype(np.int64)
+    hb.batch_sizes = r['batch_sizes']
+    hb.times = view.store.gs.times[r['comp_graph']]
+    hb.h2d_bytes = words * 4
+    return hb

@@ -115,12 +115,15 @@ class SyntheticTKG:
         # the reference's global_emb values are [1,1,h] tensors from the pre-trained global model
         self.global_emb = {t: 0.1 * torch.randn(1, 1, h_dim, generator=g) for t in self.graph_dict}
 
-    def batch(self, index, batch_size=1024, seed=999, tail_only=True):
-        """``index``-th batch of a seeded permutation (train.py:127-129 shuffles then slices).  With
-        tail_only the permutation covers the last third of the stream, where histories are full."""
+    def batch_indices(self, index, batch_size=1024, seed=999, tail_only=True):
         n = len(self.quads)
         lo = (2 * n) // 3 if tail_only else 0
         perm = np.random.RandomState(seed).permutation(np.arange(lo, n))
-        sel = perm[(index * batch_size) % max(1, len(perm) - batch_size):][:batch_size]
+        return perm[(index * batch_size) % max(1, len(perm) - batch_size):][:batch_size]
+
+    def batch(self, index, batch_size=1024, seed=999, tail_only=True):
+        """``index``-th batch of a seeded permutation (train.py:127-129 shuffles then slices).  With
+        tail_only the permutation covers the last third of the stream, where histories are full."""
+        sel = self.batch_indices(index, batch_size, seed, tail_only)
         pick = lambda lst: [lst[i] for i in sel]
         return (self.quads[sel], (pick(self.s_hist), pick(self.s_hist_t)), (pick(self.o_hist), pick(self.o_hist_t)))

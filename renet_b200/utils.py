@@ -143,11 +143,23 @@ def upload_history_batch(hb, device):
     return hb
 
 
+_GLOB_CACHE = {}
+
+
 def global_rows(global_emb, times, h, device):
-    """[T,h] matrix of global_emb[t] for the batch's distinct timestamps (utils.py:224-225 gathers
-    one row per read-out row with a .cpu() each; here: one stack per distinct timestamp)."""
-    rows = [global_emb[int(t)].reshape(-1) for t in times]
-    return torch.stack(rows).to(device=device, dtype=torch.float32).view(len(rows), h)
+    """[T,h] matrix of global_emb[t] for the batch's distinct timestamps.  The reference gathers one row per
+    read-out row with a .cpu() each (utils.py:224-225); here the dict is turned into a dense device table
+    once (cached per dict object) and a batch is one index_select."""
+    key = id(global_emb)
+    hit = _GLOB_CACHE.get(key)
+    if hit is None or hit[0] is not global_emb or hit[1] != len(global_emb) or hit[3].device != torch.device(device):
+        keys = np.asarray(sorted(int(t) for t in global_emb.keys()), dtype=np.int64)
+        table = torch.stack([global_emb[int(t)].reshape(-1) for t in keys]).to(device=device, dtype=torch.float32)
+        hit = (global_emb, len(global_emb), keys, table.view(len(keys), h))
+        _GLOB_CACHE.clear()
+        _GLOB_CACHE[key] = hit
+    idx = np.searchsorted(hit[2], np.asarray(times, dtype=np.int64))
+    return hit[3][torch.from_numpy(idx).to(device)]
 
 
 def _wrap(hb, s, r, ent_embeds, global_emb):

@@ -141,3 +141,21 @@ def test_no_cpu_fallback():
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         _lib.require_cuda(torch.zeros(3))
     assert _lib.launch_count() > 0
+
+
+def test_cpp_batcher_path_equals_list_path():
+    """RENet.encode fed with HistoryViews (flat stores + C++ batcher) == fed with the reference's lists."""
+    from renet_b200 import hoststore
+    b, m, params, glob, gd, batch, sh, oh, quads, sel, (num_e, R, h, nb) = _setup('renet_icews18_slice.npz')
+    from renet_b200 import synthetic
+    S, ST, O, OT = synthetic.build_history(quads)
+    gs = hoststore.GraphStore(gd)
+    vs = hoststore.HistoryStore(S, ST, quads[:, 0], gs).select(sel)
+    vo = hoststore.HistoryStore(O, OT, quads[:, 2], gs).select(sel)
+    m.eval()
+    with torch.no_grad():
+        for subj in (True, False):
+            a = m.encode(batch, sh, oh, gd, subject=subj)
+            c = m.encode(batch, vs, vo, gs, subject=subj)
+            for x, y in zip(a[:5], c[:5]):
+                assert torch.allclose(x.float(), y.float(), atol=1e-5)

@@ -105,3 +105,40 @@ def test_empty_and_ragged_histories():
     # all-empty batch
     hb = utils.assemble_history_batch_host([[], []], [[], []], np.asarray([1, 2]), gd)
     assert hb.graph is None and hb.S == 0
+
+
+def test_cpp_batcher_matches_numpy_path():
+    """renet_host_assemble_batch (C++) produces exactly the batch of the numpy path (same node order,
+    same CSR, same bookkeeping) on an ICEWS18-shaped stream, both directions."""
+    from renet_b200 import hoststore
+    quads, num_e, num_r = synthetic.make_quads('icews18', seed=11, num_timestamps=16)
+    S, ST, O, OT = synthetic.build_history(quads)
+    gd = synthetic.build_graph_dict(quads, num_r)
+    gs = hoststore.GraphStore(gd)
+    sel = np.random.RandomState(1).permutation(len(quads))[:300]     # includes empty histories
+    for hist, hist_t, col in ((S, ST, 0), (O, OT, 2)):
+        hs = hoststore.HistoryStore(hist, hist_t, quads[:, col], gs)
+        view = hs.select(sel)
+        buf = np.zeros(8, dtype=np.int32)
+        r = hoststore.assemble_view_raw(view, buf)
+        assert 'need_words' in r                       # too small: reports the size it needs
+        buf = np.zeros(r['need_words'], dtype=np.int32)
+        r = hoststore.assemble_view_raw(view, buf)
+        got = hoststore.split_raw(buf, r)
+        hb = utils.assemble_history_batch_host([hist[i] for i in sel], [hist_t[i] for i in sel], quads[sel][:, col], gd)
+        g = hb.graph
+        np.testing.assert_array_equal(r['s_idx'], hb.s_idx)
+        assert (r['N'], r['E'], r['S'], r['Q']) == (len(g['node_ent']), len(g['col_src']), hb.S, hb.num_seq)
+        for k in ('node_ent', 'row_ptr', 'col_src', 'col_type_s', 'col_type_o'):
+            np.testing.assert_array_equal(got[k], g[k].astype(np.int32), err_msg=k)
+        np.testing.assert_array_equal(got['norm'].view(np.float32), g['norm'])
+        readout, row_comp, row_seq, seq_start, seq_len, packed_row = hb.readout
+        for k, v in (('readout', readout), ('row_comp', row_comp), ('row_seq', row_seq), ('seq_start', seq_start),
+                     ('seq_len', seq_len), ('packed_row', packed_row)):
+            np.testing.assert_array_equal(got[k], np.asarray(v).astype(np.int32), err_msg=k)
+        np.testing.assert_array_equal(r['batch_sizes'], hb.batch_sizes)
+        np.testing.assert_array_equal(gs.times[r['comp_graph']], hb.times)
+    # all-empty batch
+    view = hs.select(np.asarray([0, 1]))
+    r = hoststore.assemble_view_raw(view, np.zeros(64, np.int32))
+    assert r['S'] == 0 and r['N'] == 0
