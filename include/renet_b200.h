@@ -101,6 +101,20 @@ int renet_rgcn_gather(const float* H, const int32_t* h_index, const float* W,
                       int64_t N, int64_t E, int32_t d_in, int32_t d_out,
                       int32_t num_bases, int32_t R2, int32_t relu, int32_t has_loop, void* stream);
 
+/* Component-resident variant of renet_rgcn_gather for batched graphs whose nodes are grouped by
+ * component (dgl.batch of sub-graphs, utils.py:238): comp_ptr [G+1] = node offsets of the components (every
+ * edge stays inside one component), comp_order [G] or NULL = launch order (largest first balances the
+ * SMs), rel_slot [R2] / hot_rel [n_hot] (n_hot <= 40, may be 0/NULL) = the relation rows to keep in shared
+ * memory (rel_slot[r] = i iff hot_rel[i] = r, else -1).  Same result as renet_rgcn_gather; shapes other than
+ * d=200/num_bases=100 fall back to it. */
+int renet_rgcn_gather_comp(const float* H, const int32_t* h_index, const float* W,
+                           const int32_t* row_ptr, const int32_t* col_src, const int32_t* col_type,
+                           const float* norm, float* Hout,
+                           const int32_t* comp_ptr, const int32_t* comp_order,
+                           const int32_t* rel_slot, const int32_t* hot_rel, int32_t n_hot,
+                           int64_t N, int64_t E, int64_t G, int32_t d_in, int32_t d_out,
+                           int32_t num_bases, int32_t R2, int32_t relu, int32_t has_loop, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * RGCN block-diagonal layer, backward (autograd of the above; the reference relies on
  * torch.autograd through bmm / index_select / DGL's reduce, train.py:139).
@@ -208,8 +222,11 @@ int renet_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_gl
  * graph in CSR form + bookkeeping packed into `out` (int32 words, one H2D copy):
  *   node_ent[N] row_ptr[N+1] col_src[E] col_type_s[E] col_type_o[E] norm[N](float bits)
  *   readout[S] row_comp[S] row_seq[S] seq_start[Q] seq_len[Q] packed_row[S]
- * comp_graph_out [G] (graph index of every component, first-appearance order), batch_sizes_out
- * [max_len], sizes = {N, E, S, Q, G, max_len, words_used, 0}.
+ *   comp_ptr[G+1] comp_order[G] rel_slot_s[R2] hot_s[n_hot_max] rel_slot_o[R2] hot_o[n_hot_max]
+ * (the last line feeds renet_rgcn_gather_comp: components largest-first, and the n_hot_max most frequent
+ * edge types of the batch for each type column).  comp_graph_out [G] (graph index of every component,
+ * first-appearance order), batch_sizes_out [max_len],
+ * sizes [10] = {N, E, S, Q, G, max_len, words_used, n_hot_s, n_hot_o, 0}.
  * Returns 0, or 1 when out_capacity < words_used (sizes is filled: grow and call again), <0 on error.
  * ---------------------------------------------------------------------------------------------- */
 int renet_host_assemble_batch(
@@ -217,7 +234,7 @@ int renet_host_assemble_batch(
     const int32_t* g_src, const int32_t* g_dst, const int32_t* g_type_s, const int32_t* g_type_o,
     const int64_t* h_samp_off, const int64_t* h_samp_entry, const int32_t* h_ent_graph, const int32_t* h_ent_srow,
     const int64_t* h_ent_off, const int32_t* h_nbr_row,
-    const int64_t* sample_idx, int64_t B, int32_t sort,
+    const int64_t* sample_idx, int64_t B, int32_t sort, int32_t R2, int32_t n_hot_max,
     int64_t* s_idx_out, int32_t* out, int64_t out_capacity, int32_t* comp_graph_out,
     int32_t* batch_sizes_out, int32_t max_len_capacity, int64_t* sizes);
 

@@ -47,11 +47,12 @@ extern "C" int renet_host_assemble_batch(
     const int64_t* h_samp_off, const int64_t* h_samp_entry, const int32_t* h_ent_graph, const int32_t* h_ent_srow, const int64_t* h_ent_off,
     const int32_t* h_nbr_row,
     // ---- batch --------------------------------------------------------------------------------------
-    const int64_t* sample_idx, int64_t B, int32_t sort,
+    const int64_t* sample_idx, int64_t B, int32_t sort, int32_t R2, int32_t n_hot_max,
     // ---- outputs --------------------------------------------------------------------------------------
     int64_t* s_idx_out, int32_t* out, int64_t out_capacity, int32_t* comp_graph_out, int32_t* batch_sizes_out,
-    int32_t max_len_capacity, int64_t* sizes /* [8]: N, E, S, Q, G, max_len, words_used, reserved */) {
-  if (B < 0 || !sizes) { renet::set_error("renet_host_assemble_batch: bad arguments"); return RENET_ERR_INVALID_ARG; }
+    int32_t max_len_capacity,
+    int64_t* sizes /* [10]: N, E, S, Q, G, max_len, words_used, n_hot_s, n_hot_o, 0 */) {
+  if (B < 0 || !sizes || R2 < 0 || n_hot_max < 0) { renet::set_error("renet_host_assemble_batch: bad arguments"); return RENET_ERR_INVALID_ARG; }
   // ---- 1. order samples by history length, descending, stable (model.py:80-81, utils.py:212-215) ----
   std::vector<int32_t> len(B);
   int max_len = 0;
@@ -129,7 +130,8 @@ extern "C" int renet_host_assemble_batch(
   // layout of `out` (int32 words):
   //  node_ent[N] row_ptr[N+1] col_src[E] col_type_s[E] col_type_o[E] norm[N](f32 bits)
   //  readout[S] row_comp[S] row_seq[S] seq_start[Q] seq_len[Q] packed_row[S]
-  const int64_t words = N + (N + 1) + 3 * E + N + 3 * S + 2 * Q + S;
+  //  comp_ptr[G+1] comp_order[G] rel_slot_s[R2] hot_s[n_hot_max] rel_slot_o[R2] hot_o[n_hot_max]
+  const int64_t words = N + (N + 1) + 3 * E + N + 3 * S + 2 * Q + S + (G + 1) + G + 2 * (int64_t)(R2 + n_hot_max);
   sizes[0] = N; sizes[1] = E; sizes[4] = G; sizes[6] = words;
   if (words > out_capacity) return 1;   // caller grows the staging buffer and retries
   int32_t* o_node = out;
@@ -186,5 +188,33 @@ extern "C" int renet_host_assemble_batch(
     batch_sizes_out[t] = n_act;
   }
   for (int64_t c = 0; c < G; ++c) comp_graph_out[c] = comp_graph[c];
+  // ---- 7. component table (largest first) and the hottest relations of this batch, for renet_rgcn_gather_comp ----
+  int32_t* o_cptr = o_packed + S;
+  int32_t* o_corder = o_cptr + G + 1;
+  for (int64_t c = 0; c <= G; ++c) o_cptr[c] = (int32_t)comp_start[c];
+  for (int64_t c = 0; c < G; ++c) o_corder[c] = (int32_t)c;
+  std::stable_sort(o_corder, o_corder + G, [&](int32_t a, int32_t b) {
+    return comp_estart[a + 1] - comp_estart[a] > comp_estart[b + 1] - comp_estart[b];
+  });
+  int32_t* o_hot = o_corder + G;
+  const int32_t* cols[2] = {o_ts, o_to};
+  std::vector<int64_t> cnt(R2);
+  std::vector<int32_t> ids(R2);
+  for (int w = 0; w < 2; ++w) {
+    int32_t* slot = o_hot + w * (R2 + n_hot_max);
+    int32_t* hot = slot + R2;
+    std::fill(cnt.begin(), cnt.end(), 0);
+    for (int64_t k = 0; k < E; ++k) {
+      const int32_t t = cols[w][k];
+      if ((uint32_t)t >= (uint32_t)R2) { renet::set_error("renet_host_assemble_batch: edge type %d out of range [0,%d)", t, R2); return RENET_ERR_INVALID_ARG; }
+      cnt[t]++;
+    }
+    for (int32_t i = 0; i < R2; ++i) { ids[i] = i; slot[i] = -1; }
+    std::stable_sort(ids.begin(), ids.end(), [&](int32_t a, int32_t b) { return cnt[a] > cnt[b]; });
+    int32_t nh = 0;
+    for (; nh < n_hot_max && nh < R2 && cnt[ids[nh]] > 0; ++nh) { hot[nh] = ids[nh]; slot[ids[nh]] = nh; }
+    for (int32_t i = nh; i < n_hot_max; ++i) hot[i] = 0;
+    sizes[7 + w] = nh;
+  }
   return RENET_OK;
 }

@@ -1,0 +1,166 @@
+// Component-resident fused gather (v3) for the RE-Net shape (d = 200, 100 blocks of 2x2).
+//
+// The batched history graph is a disjoint union of per-timestamp components (dgl.batch, utils.py:238;
+// ICEWS18: ~239 components of ~138 nodes / ~850 edges).  Every edge's source lies in the destination's
+// component, so ONE CTA per component can stage the component's feature rows in shared memory once
+// (contiguous rows of H for layer 2, gathered ent_embeds rows for layer 1) and serve all per-edge reads
+// from there: L2 traffic for features drops from E*800 B to N*800 B (the mean in-degree, ~6x).  The
+// relation block table (819 KB) does not fit, but relation popularity is heavily skewed: the K hottest
+// relations of the batch (chosen by the host batcher) are staged too and the rest are read through L1/L2.
+//
+// CTA = 512 threads = two groups of 8 warps; after staging, each group walks 16-destination tiles of the
+// component with the same balanced warp-level segmented reduction as rgcn_tile.cuh (even edge split over
+// the group's warps, register accumulation per destination, shared tile, fused epilogue).  One CTA per SM
+// (about 205 KB of dynamic shared memory); grid = number of components, scheduled largest-first so the
+// hardware block scheduler balances the SMs.
+#pragma once
+#include "common.cuh"
+#include "rgcn_tile.cuh"
+
+namespace renet {
+
+constexpr int kCompThreads = 512;
+constexpr int kCompGroups = 2;              // groups of kTileWarps warps
+constexpr int kWinRows = 144;               // feature rows staged per component (115.2 KB)
+constexpr int kHotRel = 40;                 // relation block rows staged (64 KB)
+constexpr int kCompSmemBytes = (kWinRows * 200 + kHotRel * 400 + kCompGroups * kTileNodes * 200) * 4 +
+                               kCompGroups * (kTileNodes + 1) * 4 + 16;
+
+__device__ __forceinline__ void group_barrier(int group) {
+  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kTileWarps * 32) : "memory");
+}
+
+struct EdgeRef {
+  const float* x;     // source feature row (shared or global)
+  const float* w;     // relation block row (shared or global)
+  bool x_smem, w_smem;
+};
+
+__device__ __forceinline__ void load_edge_ref(EdgeData& d, const EdgeRef& r, int lane) {
+  const float* xp = r.x + 2 * lane;
+  const float* wp = r.w + 4 * lane;
+  if (r.x_smem) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d.h[k] = *reinterpret_cast<const float2*>(xp + 50 * k);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d.h[k] = ldg_f2_stream(xp + 50 * k);
+  }
+  if (r.w_smem) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d.w[k] = *reinterpret_cast<const float4*>(wp + 100 * k);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d.w[k] = ldg_f4(wp + 100 * k);
+  }
+}
+
+// One 16-destination tile, processed by one 8-warp group.  `win` holds rows [win_lo, win_lo + win_n) of the
+// (logical) feature matrix; `wc` holds the hot relation rows, rel_slot maps relation -> slot or -1.
+template <bool TRANSPOSE, bool INDEXED, bool EDGE_SCALE>
+__device__ __forceinline__ void comp_tile_accumulate(float (*agg)[200], const int* s_rp, int nv, int gwarp,
+                                                     const float* __restrict__ X,
+                                                     const int32_t* __restrict__ x_index,
+                                                     const float* __restrict__ W,
+                                                     const int32_t* __restrict__ col_a,
+                                                     const int32_t* __restrict__ col_type,
+                                                     const float* __restrict__ scale, const float* win, int win_lo,
+                                                     int win_n, const float* wc,
+                                                     const int32_t* __restrict__ rel_slot) {
+  const int lane = threadIdx.x & 31;
+  const bool active = lane < 25;
+  const int ebeg = s_rp[0], eend = s_rp[nv];
+  const int chunk = (eend - ebeg + kTileWarps - 1) / kTileWarps;
+  const int e0 = ebeg + gwarp * chunk;
+  const int e1 = min(eend, e0 + chunk);
+  if (e0 >= e1) return;
+  int node = 0;
+  while (s_rp[node + 1] <= e0) ++node;
+  int node_end = s_rp[node + 1];
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  auto flush = [&](int nd) {
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        atomicAdd(&agg[nd][2 * (lane + 25 * k)], acc[2 * k]);
+        atomicAdd(&agg[nd][2 * (lane + 25 * k) + 1], acc[2 * k + 1]);
+        acc[2 * k] = acc[2 * k + 1] = 0.f;
+      }
+    }
+  };
+  auto advance = [&](int e) {
+    if (e >= node_end) {
+      flush(node);
+      do { ++node; node_end = s_rp[node + 1]; } while (e >= node_end);
+    }
+  };
+  auto make_ref = [&](int s, int slot, int t) {
+    EdgeRef r;
+    const int local = s - win_lo;
+    r.x_smem = (unsigned)local < (unsigned)win_n;
+    if (r.x_smem) {
+      r.x = win + local * 200;
+    } else {
+      const int64_t row = INDEXED ? (int64_t)__ldg(x_index + s) : s;
+      r.x = X + row * 200;
+    }
+    r.w_smem = slot >= 0;
+    r.w = r.w_smem ? (wc + slot * 400) : (W + (int64_t)t * 400);
+    return r;
+  };
+
+  for (int base = e0; base < e1; base += 32) {
+    const int e = base + lane;
+    int my_s = 0, my_t = 0, my_slot = -1;
+    float my_sc = 1.f;
+    if (e < e1) {
+      my_s = __ldg(col_a + e);
+      my_t = __ldg(col_type + e);
+      if (rel_slot != nullptr) my_slot = __ldg(rel_slot + my_t);
+      if (EDGE_SCALE) my_sc = __ldg(scale + my_s);
+    }
+    const int cnt = min(32, e1 - base);
+    for (int j = 0; j < cnt; j += 2) {
+      const int jb = min(j + 1, cnt - 1);
+      const EdgeRef ra = make_ref(__shfl_sync(0xffffffffu, my_s, j), __shfl_sync(0xffffffffu, my_slot, j),
+                                  __shfl_sync(0xffffffffu, my_t, j));
+      const EdgeRef rb = make_ref(__shfl_sync(0xffffffffu, my_s, jb), __shfl_sync(0xffffffffu, my_slot, jb),
+                                  __shfl_sync(0xffffffffu, my_t, jb));
+      const float ca = EDGE_SCALE ? __shfl_sync(0xffffffffu, my_sc, j) : 1.f;
+      const float cb = EDGE_SCALE ? __shfl_sync(0xffffffffu, my_sc, jb) : 1.f;
+      EdgeData da, db;
+      if (active) {
+        load_edge_ref(da, ra, lane);
+        load_edge_ref(db, rb, lane);
+      }
+      advance(base + j);
+      if (active) fma_edge<TRANSPOSE>(acc, da, ca);
+      if (j + 1 < cnt) {
+        advance(base + j + 1);
+        if (active) fma_edge<TRANSPOSE>(acc, db, cb);
+      }
+    }
+  }
+  flush(node);
+}
+
+// Stage the component's rows and the hot relation rows.  All kCompThreads threads.
+template <bool INDEXED>
+__device__ __forceinline__ void comp_stage(float* win, float* wc, const float* __restrict__ X,
+                                           const int32_t* __restrict__ x_index, const float* __restrict__ W,
+                                           const int32_t* __restrict__ hot_rel, int n_hot, int win_lo, int win_n) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < win_n * 50; i += kCompThreads) {
+    const int r = i / 50, c = (i % 50) * 4;
+    const int64_t row = INDEXED ? (int64_t)__ldg(x_index + win_lo + r) : (win_lo + r);
+    *reinterpret_cast<float4*>(win + r * 200 + c) = ldg_f4_stream(X + row * 200 + c);
+  }
+  for (int i = tid; i < n_hot * 100; i += kCompThreads) {
+    const int r = i / 100, c = (i % 100) * 4;
+    *reinterpret_cast<float4*>(wc + r * 400 + c) = ldg_f4(W + (int64_t)__ldg(hot_rel + r) * 400 + c);
+  }
+}
+
+}  // namespace renet

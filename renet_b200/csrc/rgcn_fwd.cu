@@ -12,6 +12,7 @@
 // warp-level segmented reduction into a shared tile, fused norm / self-loop / activation epilogue.
 #include "common.cuh"
 #include "rgcn_tile.cuh"
+#include "rgcn_comp.cuh"
 
 namespace renet {
 namespace {
@@ -50,6 +51,58 @@ rgcn_gather_d200_kernel(const float* __restrict__ H, const int32_t* __restrict__
     }
     if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
     *reinterpret_cast<float2*>(op) = o;
+  }
+}
+
+// Component-resident version (rgcn_comp.cuh): one CTA per component, features and hot relation rows staged
+// in shared memory once, two 8-warp groups walking 16-destination tiles.
+template <bool RELU, bool HAS_LOOP, bool INDEXED>
+__global__ void __launch_bounds__(kCompThreads, 1)
+rgcn_gather_comp_kernel(const float* __restrict__ H, const int32_t* __restrict__ h_index,
+                        const float* __restrict__ W, const int32_t* __restrict__ row_ptr,
+                        const int32_t* __restrict__ col_src, const int32_t* __restrict__ col_type,
+                        const float* __restrict__ norm, float* __restrict__ Hout,
+                        const int32_t* __restrict__ comp_ptr, const int32_t* __restrict__ comp_order,
+                        const int32_t* __restrict__ rel_slot, const int32_t* __restrict__ hot_rel, int n_hot) {
+  extern __shared__ __align__(16) float csm[];
+  float* win = csm;
+  float* wc = win + kWinRows * 200;
+  float(*agg)[kTileNodes][200] = reinterpret_cast<float(*)[kTileNodes][200]>(wc + kHotRel * 400);
+  int* s_rp_all = reinterpret_cast<int*>(wc + kHotRel * 400 + kCompGroups * kTileNodes * 200);
+  const int tid = threadIdx.x;
+  const int comp = comp_order != nullptr ? __ldg(comp_order + blockIdx.x) : blockIdx.x;
+  const int v_lo = __ldg(comp_ptr + comp), v_hi = __ldg(comp_ptr + comp + 1);
+  const int win_n = min(kWinRows, v_hi - v_lo);
+  comp_stage<INDEXED>(win, wc, H, h_index, W, hot_rel, n_hot, v_lo, win_n);
+  __syncthreads();
+  const int group = tid / (kTileWarps * 32), gtid = tid % (kTileWarps * 32), gwarp = gtid >> 5;
+  float(*my_agg)[200] = agg[group];
+  int* s_rp = s_rp_all + group * (kTileNodes + 1);
+  const int n_tiles = (v_hi - v_lo + kTileNodes - 1) / kTileNodes;
+  for (int tile = group; tile < n_tiles; tile += kCompGroups) {
+    const int v0 = v_lo + tile * kTileNodes;
+    const int nv = min(kTileNodes, v_hi - v0);
+    for (int i = gtid; i < kTileNodes * 200; i += kTileWarps * 32) (&my_agg[0][0])[i] = 0.f;
+    if (gtid <= nv) s_rp[gtid] = __ldg(row_ptr + v0 + gtid);
+    group_barrier(group);
+    comp_tile_accumulate<false, INDEXED, false>(my_agg, s_rp, nv, gwarp, H, h_index, W, col_src, col_type, nullptr,
+                                                win, v_lo, win_n, wc, n_hot > 0 ? rel_slot : nullptr);
+    group_barrier(group);
+    for (int i = gtid; i < nv * 100; i += kTileWarps * 32) {
+      const int r = i / 100, c = (i % 100) * 2;
+      const int v = v0 + r;
+      const float2 a = *reinterpret_cast<const float2*>(&my_agg[r][c]);
+      const float nvv = __ldg(norm + v);
+      float* op = Hout + (int64_t)v * 200 + c;
+      float2 o = make_float2(a.x * nvv, a.y * nvv);
+      if (HAS_LOOP) {
+        const float2 l = *reinterpret_cast<const float2*>(op);
+        o.x += l.x; o.y += l.y;
+      }
+      if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
+      *reinterpret_cast<float2*>(op) = o;
+    }
+    group_barrier(group);
   }
 }
 
@@ -121,6 +174,35 @@ int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, c
         H, h_index, W, row_ptr, col_src, col_type, norm, Hout, N, d_in, d_out, nb, relu, has_loop, passthrough);
     RENET_CHECK_LAUNCH("rgcn_gather_generic_kernel");
   }
+  return RENET_OK;
+}
+
+int launch_rgcn_gather_comp(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
+                            const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout,
+                            const int32_t* comp_ptr, const int32_t* comp_order, const int32_t* rel_slot,
+                            const int32_t* hot_rel, int n_hot, int64_t G, int relu, int has_loop,
+                            cudaStream_t stream) {
+  if (G == 0) return RENET_OK;
+  static bool attr_set = false;
+#define RENET_FOR_ALL_COMP(X) X(false, false, false) X(false, false, true) X(false, true, false) X(false, true, true) \
+    X(true, false, false) X(true, false, true) X(true, true, false) X(true, true, true)
+  if (!attr_set) {
+#define RENET_SET_ATTR(R, L, I)                                                                                 \
+    RENET_CHECK_CUDA(cudaFuncSetAttribute(rgcn_gather_comp_kernel<R, L, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          kCompSmemBytes));
+    RENET_FOR_ALL_COMP(RENET_SET_ATTR)
+#undef RENET_SET_ATTR
+    attr_set = true;
+  }
+  const int key = (relu ? 4 : 0) | (has_loop ? 2 : 0) | (h_index ? 1 : 0);
+#define RENET_LAUNCH_COMP(R, L, I)                                                                              \
+  if (key == ((R ? 4 : 0) | (L ? 2 : 0) | (I ? 1 : 0)))                                                          \
+    rgcn_gather_comp_kernel<R, L, I><<<(unsigned)G, kCompThreads, kCompSmemBytes, stream>>>(                     \
+        H, h_index, W, row_ptr, col_src, col_type, norm, Hout, comp_ptr, comp_order, rel_slot, hot_rel, n_hot);
+  RENET_FOR_ALL_COMP(RENET_LAUNCH_COMP)
+#undef RENET_LAUNCH_COMP
+#undef RENET_FOR_ALL_COMP
+  RENET_CHECK_LAUNCH("rgcn_gather_comp_kernel");
   return RENET_OK;
 }
 

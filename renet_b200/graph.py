@@ -116,21 +116,33 @@ class BatchedHistoryGraph:
 
     Equivalent of ``dgl.batch(g_list)`` + ``move_dgl_to_cuda`` (reference utils.py:237-241)."""
 
-    def __init__(self, node_ent, norm, row_ptr, col_src, col_type_s, col_type_o, comp_sizes, device):
+    def __init__(self, node_ent, norm, row_ptr, col_src, col_type_s, col_type_o, comp_sizes, device, extras=None):
         self.device = torch.device(device)
         self.N = int(len(node_ent))
         self.E = int(len(col_src))
         self.comp_sizes = comp_sizes
         # one pinned staging buffer -> one H2D copy
-        i32 = np.concatenate((node_ent.astype(np.int32), row_ptr.astype(np.int32), col_src.astype(np.int32),
-                              col_type_s.astype(np.int32), col_type_o.astype(np.int32)))
+        parts = [node_ent, row_ptr, col_src, col_type_s, col_type_o]
+        names = ['comp_ptr', 'comp_order', 'rel_slot_s', 'hot_s', 'rel_slot_o', 'hot_o']
+        if extras is not None:
+            parts += [extras[k] for k in names]
+        i32 = np.concatenate([np.asarray(p).astype(np.int32) for p in parts])
         dev = _to_device(torch.from_numpy(i32), self.device)
         o = 0
         self.node_ent = dev[o:o + self.N]; o += self.N
         self.row_ptr = dev[o:o + self.N + 1]; o += self.N + 1
         self.col_src = dev[o:o + self.E]; o += self.E
         self.col_type_s = dev[o:o + self.E]; o += self.E
-        self.col_type_o = dev[o:o + self.E]
+        self.col_type_o = dev[o:o + self.E]; o += self.E
+        self.comp, self.G = None, 0
+        if extras is not None:
+            t = {}
+            for k in names:
+                n = len(extras[k])
+                t[k] = dev[o:o + n]; o += n
+            self.G = len(extras['comp_order'])
+            self.comp = {False: (t['comp_ptr'], t['comp_order'], t['rel_slot_s'], t['hot_s'], int(extras['n_hot_s'])),
+                         True: (t['comp_ptr'], t['comp_order'], t['rel_slot_o'], t['hot_o'], int(extras['n_hot_o']))}
         self.norm = _to_device(torch.from_numpy(np.ascontiguousarray(norm, dtype=np.float32)), self.device)
         self.h2d_bytes = i32.nbytes + self.N * 4
         self.ndata = _Frame(norm=self.norm.view(-1, 1), id=self.node_ent.view(-1, 1))
@@ -154,6 +166,7 @@ class BatchedHistoryGraph:
         g.ndata = _Frame(norm=g.norm.view(-1, 1), id=g.node_ent.view(-1, 1))
         g.h_index = g.h_table = None
         g._bwd = {}
+        g.comp, g.G = None, 0
         return g
 
     def number_of_nodes(self):

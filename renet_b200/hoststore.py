@@ -22,6 +22,7 @@ from .graph import BatchedHistoryGraph, _Frame, as_history_graph
 from .utils import HistoryBatch
 
 MAX_LEN = 16
+N_HOT = 40          # relation rows renet_rgcn_gather_comp keeps in shared memory (kHotRel)
 
 
 def _p(a):
@@ -49,6 +50,7 @@ class GraphStore:
         self.type_s = cat([g.type_s for g in graphs], np.int32)
         self.type_o = cat([g.type_o for g in graphs], np.int32)
         self.graphs = graphs
+        self.num_types = int(max(self.type_s.max(), self.type_o.max())) + 1 if len(self.type_s) else 1
 
     def __getitem__(self, t):
         return self.graph_dict[t]
@@ -151,17 +153,17 @@ def assemble_view_raw(view, out, sort=True):
     s_idx = np.empty(B, dtype=np.int64)
     comp_graph = np.empty(len(gs.times), dtype=np.int32)
     bsz = np.zeros(MAX_LEN, dtype=np.int32)
-    sizes = np.zeros(8, dtype=np.int64)
+    sizes = np.zeros(10, dtype=np.int64)
     rc = L.renet_host_assemble_batch(
         len(gs.times), _p(gs.node_off), _p(gs.node_ent), _p(gs.edge_off), _p(gs.src), _p(gs.dst), _p(gs.type_s),
         _p(gs.type_o), _p(hs.samp_off), _p(hs.samp_entry), _p(hs.ent_graph), _p(hs.ent_srow), _p(hs.ent_off), _p(hs.nbr_row),
-        _p(view.sample_idx), B, int(sort), _p(s_idx), _p(out), out.size, _p(comp_graph), _p(bsz), MAX_LEN, _p(sizes))
+        _p(view.sample_idx), B, int(sort), gs.num_types, N_HOT, _p(s_idx), _p(out), out.size, _p(comp_graph), _p(bsz), MAX_LEN, _p(sizes))
     if rc == 1:
         return {'need_words': int(sizes[6])}
     _lib.check(rc, 'renet_host_assemble_batch')
     N, E, S, Q, G, max_len, words = (int(x) for x in sizes[:7])
     return dict(N=N, E=E, S=S, Q=Q, G=G, max_len=max_len, words=words, s_idx=s_idx, comp_graph=comp_graph[:G],
-                batch_sizes=bsz[:max_len].copy())
+                batch_sizes=bsz[:max_len].copy(), R2=gs.num_types, n_hot_s=int(sizes[7]), n_hot_o=int(sizes[8]))
 
 
 def split_raw(buf, r):
@@ -171,7 +173,8 @@ def split_raw(buf, r):
     out = {}
     for name, n in (('node_ent', N), ('row_ptr', N + 1), ('col_src', E), ('col_type_s', E), ('col_type_o', E),
                     ('norm', N), ('readout', S), ('row_comp', S), ('row_seq', S), ('seq_start', Q), ('seq_len', Q),
-                    ('packed_row', S)):
+                    ('packed_row', S), ('comp_ptr', r['G'] + 1), ('comp_order', r['G']), ('rel_slot_s', r['R2']),
+                    ('hot_s', N_HOT), ('rel_slot_o', r['R2']), ('hot_o', N_HOT)):
         out[name] = buf[o:o + n]
         o += n
     return out
@@ -179,7 +182,9 @@ def split_raw(buf, r):
 
 def assemble_view(view, device, sort=True):
     """HistoryView -> HistoryBatch on ``device`` through the C++ batcher (one pinned H2D copy)."""
-    st = _staging.setdefault(str(device), _Staging())
+    st = _staging.get(str(device))
+    if st is None:
+        st = _staging[str(device)] = _Staging()
     slot, buf = st.next()
     r = assemble_view_raw(view, buf.numpy(), sort)
     if 'need_words' in r:
@@ -207,6 +212,9 @@ def assemble_view(view, device, sort=True):
     g.ndata = _Frame(norm=g.norm.view(-1, 1), id=g.node_ent.view(-1, 1))
     g.h_index = g.h_table = None
     g._bwd = {}
+    g.G = r['G']
+    g.comp = {False: (d['comp_ptr'], d['comp_order'], d['rel_slot_s'], d['hot_s'], r['n_hot_s']),
+              True: (d['comp_ptr'], d['comp_order'], d['rel_slot_o'], d['hot_o'], r['n_hot_o'])}
     g.seq_len_dev = d['seq_len']
     hb.graph = g
     hb.readout, hb.row_glob, hb.row_seq = d['readout'], d['row_comp'], d['row_seq']

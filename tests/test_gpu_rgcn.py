@@ -179,3 +179,50 @@ def test_full_size_properties(G):
     # relu(layer) == max(layer, 0) (up to the summation order of partial sums of split destinations)
     r = G.layer_fwd(H, None, W, Wl, rp, cs, ct, norm, N, E, 200, 200, 100, True)
     assert float((r - torch.clamp_min(a, 0)).abs().max()) < 1e-5 and float(r.min()) >= 0.0
+
+
+def test_component_resident_kernel_vs_oracle(G):
+    """renet_rgcn_gather_comp on a batched graph with components larger than the shared-memory window
+    (144 rows), with and without hot relations / launch order, against the CPU oracle and the tile kernel."""
+    from renet_b200 import _lib, utils
+    L = _lib.lib()
+    rng = np.random.RandomState(5)
+    sizes = [300, 17, 144, 145, 1, 64, 250]
+    comp_start = np.concatenate(([0], np.cumsum(sizes)))
+    N, R2 = int(comp_start[-1]), 96
+    src, dst, comp_edges = [], [], []
+    for c, n in enumerate(sizes):
+        e = n * 7 if n > 1 else 3
+        src.append(comp_start[c] + rng.randint(0, n, e)); dst.append(comp_start[c] + rng.randint(0, n, e))
+        comp_edges.append(e)
+    src, dst = np.concatenate(src), np.concatenate(dst)
+    order = np.argsort(dst, kind='stable')
+    src, dst = src[order], dst[order]
+    et = (rng.zipf(1.4, len(src)) % R2).astype(np.int64)
+    indeg = np.bincount(dst, minlength=N)
+    row_ptr = np.concatenate(([0], np.cumsum(indeg)))
+    norm = (1.0 / np.maximum(indeg, 1)).astype(np.float32)
+    comp_edges = np.bincount(np.searchsorted(comp_start[1:], dst, side='right'), minlength=len(sizes))
+    ex = utils.component_extras(comp_start, comp_edges, et, et, num_types=R2)
+    torch.manual_seed(2)
+    ent = torch.randn(500, 200) * 0.3
+    node_ent = rng.randint(0, 500, N)
+    W, Wl = torch.randn(R2, 400) * 0.1, torch.randn(200, 200) * 0.07
+    ref = restate.rgcn_block_layer(ent[t(node_ent)], W, Wl, t(src), t(dst), t(et), t(norm), True, 100)
+    d = lambda a, dt=torch.int32: G.d(np.asarray(a), dt)
+    rp, cs, ct, nrm, idx = d(row_ptr), d(src), d(et), G.d(norm), d(node_ent)
+    Wd, Wld, entd = W.to(G.DEV), Wl.to(G.DEV), ent.to(G.DEV)
+    tile = G.layer_fwd(entd, idx, Wd, Wld, rp, cs, ct, nrm, N, len(src), 200, 200, 100, True)
+    assert rel_err(tile.cpu().numpy(), ref.numpy()) < TOL
+    for use_hot, use_order in ((True, True), (False, False), (True, False)):
+        out = torch.empty(N, 200, device=G.DEV)
+        _lib.check(L.renet_selfloop_gemm(_lib.ptr(entd), _lib.ptr(idx), _lib.ptr(Wld), _lib.ptr(out), N, 200, 200,
+                                         _lib.stream()), 'gemm')
+        rc = L.renet_rgcn_gather_comp(_lib.ptr(entd), _lib.ptr(idx), _lib.ptr(Wd), _lib.ptr(rp), _lib.ptr(cs),
+                                      _lib.ptr(ct), _lib.ptr(nrm), _lib.ptr(out), _lib.ptr(d(ex['comp_ptr'])),
+                                      _lib.ptr(d(ex['comp_order'])) if use_order else None,
+                                      _lib.ptr(d(ex['rel_slot_s'])) if use_hot else None,
+                                      _lib.ptr(d(ex['hot_s'])) if use_hot else None, ex['n_hot_s'] if use_hot else 0,
+                                      N, len(src), len(sizes), 200, 200, 100, R2, 1, 1, _lib.stream())
+        _lib.check(rc, 'renet_rgcn_gather_comp')
+        assert rel_err(out.cpu().numpy(), ref.numpy()) < TOL, (use_hot, use_order)

@@ -138,6 +138,14 @@ def test_cpp_batcher_matches_numpy_path():
             np.testing.assert_array_equal(got[k], np.asarray(v).astype(np.int32), err_msg=k)
         np.testing.assert_array_equal(r['batch_sizes'], hb.batch_sizes)
         np.testing.assert_array_equal(gs.times[r['comp_graph']], hb.times)
+        ex = utils.component_extras(np.concatenate(([0], np.cumsum(g['comp_sizes']))),
+                                    np.bincount(np.searchsorted(np.cumsum(g['comp_sizes']), np.repeat(np.arange(len(g['node_ent'])), np.diff(g['row_ptr'])), side='right'), minlength=len(g['comp_sizes'])),
+                                    g['col_type_s'], g['col_type_o'], num_types=gs.num_types)
+        for k in ('comp_ptr', 'comp_order', 'rel_slot_s', 'hot_s', 'rel_slot_o', 'hot_o'):
+            np.testing.assert_array_equal(got[k], ex[k], err_msg=k)
+            np.testing.assert_array_equal(g['extras'][k][:len(ex[k])] if k.startswith('comp') else ex[k], ex[k])
+        assert (r['n_hot_s'], r['n_hot_o']) == (ex['n_hot_s'], ex['n_hot_o'])
+        assert r['n_hot_s'] > 0 and np.all(got['rel_slot_s'][got['hot_s'][:r['n_hot_s']]] == np.arange(r['n_hot_s']))
     # all-empty batch
     view = hs.select(np.asarray([0, 1]))
     r = hoststore.assemble_view_raw(view, np.zeros(64, np.int32))
