@@ -46,6 +46,9 @@ int64_t renet_launch_count(void);
  * renet_set_gemm_engine returns the previous engine. */
 int renet_set_gemm_engine(int engine);
 int renet_get_gemm_engine(void);
+/* Tuning knob for renet_rgcn_gather's d=200 kernel (tile size / occupancy variants, see rgcn_fwd.cu);
+ * results are identical across variants.  Returns the previous value. */
+int renet_set_gather_variant(int variant);
 
 /* ------------------------------------------------------------------------------------------------
  * Graph preprocessing.  Replaces what DGL does inside g.update_all (RGCN.py:91) to find the

@@ -20,6 +20,7 @@ SIGNATURES = {
     'renet_launch_count': (_i64, []),
     'renet_set_gemm_engine': (ctypes.c_int, [ctypes.c_int]),
     'renet_get_gemm_engine': (ctypes.c_int, []),
+    'renet_set_gather_variant': (ctypes.c_int, [ctypes.c_int]),
     'renet_csr_workspace_bytes': (_i64, [_i64, _i64]),
     'renet_build_csr': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     'renet_rgcn_block_fwd': (ctypes.c_int, [_vp] * 9 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -61,6 +61,8 @@ int launch_pack_inputs(const float* H2, const int32_t* readout, const int32_t* r
 
 int gemm_mode();
 int set_gemm_mode(int m);
+int gather_variant();
+int set_gather_variant(int v);
 
 namespace {
 
@@ -106,6 +108,7 @@ const char* renet_last_error(void) { return g_err; }
 int64_t renet_launch_count(void) { return g_launches.load(); }
 int renet_set_gemm_engine(int engine) { return set_gemm_mode(engine); }
 int renet_get_gemm_engine(void) { return gemm_mode(); }
+int renet_set_gather_variant(int variant) { return set_gather_variant(variant); }
 
 int64_t renet_csr_workspace_bytes(int64_t N, int64_t E) {
   size_t cub_bytes = 0;

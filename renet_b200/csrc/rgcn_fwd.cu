@@ -10,6 +10,8 @@
 // Fast path (d_in = d_out = 200, num_bases = 100, 2x2 blocks -- the only shape RE-Net uses,
 // model.py:36): see rgcn_tile.cuh.  One CTA = 16 destination rows, edges split evenly over 8 warps,
 // warp-level segmented reduction into a shared tile, fused norm / self-loop / activation epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "rgcn_tile.cuh"
 #include "rgcn_comp.cuh"
@@ -17,18 +19,18 @@
 namespace renet {
 namespace {
 
-template <bool RELU, bool HAS_LOOP, bool INDEXED>
-__global__ void __launch_bounds__(kTileWarps * 32)
+template <bool RELU, bool HAS_LOOP, bool INDEXED, int NODES = kTileNodes, int MINB = 1>
+__global__ void __launch_bounds__(kTileWarps * 32, MINB)
 rgcn_gather_d200_kernel(const float* __restrict__ H, const int32_t* __restrict__ h_index,
                         const float* __restrict__ W, const int32_t* __restrict__ row_ptr,
                         const int32_t* __restrict__ col_src, const int32_t* __restrict__ col_type,
                         const float* __restrict__ norm, float* __restrict__ Hout, int N, int passthrough) {
-  __shared__ __align__(16) float agg[kTileNodes][200];
-  __shared__ int s_rp[kTileNodes + 1];
+  __shared__ __align__(16) float agg[NODES][200];
+  __shared__ int s_rp[NODES + 1];
   const int tid = threadIdx.x;
-  const int v0 = blockIdx.x * kTileNodes;
-  const int nv = min(kTileNodes, N - v0);
-  for (int i = tid; i < kTileNodes * 200; i += kTileWarps * 32) (&agg[0][0])[i] = 0.f;
+  const int v0 = blockIdx.x * NODES;
+  const int nv = min(NODES, N - v0);
+  for (int i = tid; i < NODES * 200; i += kTileWarps * 32) (&agg[0][0])[i] = 0.f;
   if (tid <= nv) s_rp[tid] = __ldg(row_ptr + v0 + tid);
   __syncthreads();
   tile_accumulate<false, INDEXED, false>(agg, s_rp, nv, H, h_index, W, col_src, col_type, nullptr);
@@ -140,6 +142,22 @@ __global__ void rgcn_gather_generic_kernel(const float* __restrict__ H, const in
 
 }  // namespace
 
+// experiment knob (RENET_GATHER_VARIANT / renet_set_gather_variant): 0 = 16 nodes per CTA, 1 = 16 nodes + at
+// least 4 CTAs/SM, 2 = 32 nodes, 3 = 32 nodes + 4 CTAs/SM, 4 = prefer the component-resident kernel
+static int g_gather_variant = -1;
+int gather_variant() {
+  if (g_gather_variant < 0) {
+    const char* e = getenv("RENET_GATHER_VARIANT");
+    g_gather_variant = e ? atoi(e) : 0;
+  }
+  return g_gather_variant;
+}
+int set_gather_variant(int v) {
+  const int prev = gather_variant();
+  g_gather_variant = v;
+  return prev;
+}
+
 int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
                        const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout,
                        int64_t N, int64_t E, int d_in, int d_out, int nb, int relu, int has_loop,
@@ -150,11 +168,17 @@ int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, c
                     ((reinterpret_cast<uintptr_t>(H) | reinterpret_cast<uintptr_t>(W) |
                       reinterpret_cast<uintptr_t>(Hout)) & 15) == 0;
   if (fast) {
-    const unsigned grid = (unsigned)((N + kTileNodes - 1) / kTileNodes);
     const unsigned block = kTileWarps * 32;
-#define RENET_LAUNCH_GATHER(R, L, I)                                                                   \
-  rgcn_gather_d200_kernel<R, L, I><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, \
-                                                               norm, Hout, (int)N, passthrough)
+    const int variant = gather_variant();
+    const int nodes = (variant == 2 || variant == 3) ? 32 : 16;
+    const unsigned grid = (unsigned)((N + nodes - 1) / nodes);
+#define RENET_LAUNCH_GATHER(R, L, I)                                                                            \
+  switch (variant) {                                                                                            \
+    case 1: rgcn_gather_d200_kernel<R, L, I, 16, 4><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough); break; \
+    case 2: rgcn_gather_d200_kernel<R, L, I, 32, 3><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough); break; \
+    case 3: rgcn_gather_d200_kernel<R, L, I, 32, 4><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough); break; \
+    default: rgcn_gather_d200_kernel<R, L, I, 16, 3><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough); break; \
+  }
     const int key = (relu ? 4 : 0) | (has_loop ? 2 : 0) | (h_index ? 1 : 0);
     switch (key) {
       case 0: RENET_LAUNCH_GATHER(false, false, false); break;

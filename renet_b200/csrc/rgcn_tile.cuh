@@ -19,7 +19,7 @@
 
 namespace renet {
 
-constexpr int kTileNodes = 16;
+constexpr int kTileNodes = 16;   // default tile; the forward kernel is also instantiated with 32
 constexpr int kTileWarps = 8;
 
 __device__ __forceinline__ float2 ldg_f2_stream(const float* p) {
@@ -63,7 +63,7 @@ __device__ __forceinline__ void fma_edge(float (&acc)[8], const EdgeData& d, flo
 // Accumulate the tile's messages into `agg` (shared, [kTileNodes][200], zeroed by this function).
 // s_rp: shared copy of row_ptr[v0 .. v0+nv].  EDGE_SCALE: multiply each message by scale[col_a[e]]
 // (backward: norm of the edge's destination).
-template <bool TRANSPOSE, bool INDEXED, bool EDGE_SCALE>
+template <bool TRANSPOSE, bool INDEXED, bool EDGE_SCALE, bool SMEM_IDX = false>
 __device__ __forceinline__ void tile_accumulate(float (*agg)[200], const int* s_rp, int nv,
                                                 const float* __restrict__ X, const int32_t* __restrict__ x_index,
                                                 const float* __restrict__ W, const int32_t* __restrict__ col_a,

@@ -214,15 +214,21 @@ def test_component_resident_kernel_vs_oracle(G):
     Wd, Wld, entd = W.to(G.DEV), Wl.to(G.DEV), ent.to(G.DEV)
     tile = G.layer_fwd(entd, idx, Wd, Wld, rp, cs, ct, nrm, N, len(src), 200, 200, 100, True)
     assert rel_err(tile.cpu().numpy(), ref.numpy()) < TOL
+    cptr_d, cord_d, slot_d, hot_d = d(ex['comp_ptr']), d(ex['comp_order']), d(ex['rel_slot_s']), d(ex['hot_s'])
     for use_hot, use_order in ((True, True), (False, False), (True, False)):
         out = torch.empty(N, 200, device=G.DEV)
         _lib.check(L.renet_selfloop_gemm(_lib.ptr(entd), _lib.ptr(idx), _lib.ptr(Wld), _lib.ptr(out), N, 200, 200,
                                          _lib.stream()), 'gemm')
         rc = L.renet_rgcn_gather_comp(_lib.ptr(entd), _lib.ptr(idx), _lib.ptr(Wd), _lib.ptr(rp), _lib.ptr(cs),
-                                      _lib.ptr(ct), _lib.ptr(nrm), _lib.ptr(out), _lib.ptr(d(ex['comp_ptr'])),
-                                      _lib.ptr(d(ex['comp_order'])) if use_order else None,
-                                      _lib.ptr(d(ex['rel_slot_s'])) if use_hot else None,
-                                      _lib.ptr(d(ex['hot_s'])) if use_hot else None, ex['n_hot_s'] if use_hot else 0,
+                                      _lib.ptr(ct), _lib.ptr(nrm), _lib.ptr(out), _lib.ptr(cptr_d),
+                                      _lib.ptr(cord_d) if use_order else None,
+                                      _lib.ptr(slot_d) if use_hot else None,
+                                      _lib.ptr(hot_d) if use_hot else None, ex['n_hot_s'] if use_hot else 0,
                                       N, len(src), len(sizes), 200, 200, 100, R2, 1, 1, _lib.stream())
         _lib.check(rc, 'renet_rgcn_gather_comp')
         assert rel_err(out.cpu().numpy(), ref.numpy()) < TOL, (use_hot, use_order)
+    # every tile-kernel variant gives the same result
+    for variant in (1, 2, 3, 0):
+        L.renet_set_gather_variant(variant)
+        tile = G.layer_fwd(entd, idx, Wd, Wld, rp, cs, ct, nrm, N, len(src), 200, 200, 100, True)
+        assert rel_err(tile.cpu().numpy(), ref.numpy()) < TOL, variant
