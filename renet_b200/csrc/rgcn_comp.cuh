@@ -21,10 +21,10 @@ namespace renet {
 
 constexpr int kCompThreads = 512;
 constexpr int kCompGroups = 2;              // groups of kTileWarps warps
-constexpr int kWinRows = 144;               // feature rows staged per component (115.2 KB)
+constexpr int kWinRows = 128;               // feature rows staged per component (102.4 KB)
 constexpr int kHotRel = 40;                 // relation block rows staged (64 KB)
-constexpr int kCompSmemBytes = (kWinRows * 200 + kHotRel * 400 + kCompGroups * kTileNodes * 200) * 4 +
-                               kCompGroups * (kTileNodes + 1) * 4 + 16;
+constexpr int kCompSmemBytes = (kWinRows * 200 + kHotRel * 400 + 2 * kCompGroups * kTileNodes * 200 +
+                                kCompGroups * kTileNodes) * 4 + kCompGroups * (kTileNodes + 1) * 4 + 16;
 
 __device__ __forceinline__ void group_barrier(int group) {
   asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kTileWarps * 32) : "memory");

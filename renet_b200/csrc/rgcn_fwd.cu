@@ -26,16 +26,20 @@ rgcn_gather_d200_kernel(const float* __restrict__ H, const int32_t* __restrict__
                         const int32_t* __restrict__ col_src, const int32_t* __restrict__ col_type,
                         const float* __restrict__ norm, float* __restrict__ Hout, int N, int passthrough) {
   __shared__ __align__(16) float agg[NODES][200];
+  __shared__ __align__(16) float loopbuf[HAS_LOOP ? NODES : 1][200];
+  __shared__ float normbuf[NODES];
   __shared__ int s_rp[NODES + 1];
   const int tid = threadIdx.x;
   const int v0 = blockIdx.x * NODES;
   const int nv = min(NODES, N - v0);
+  tile_prefetch_epilogue(loopbuf, normbuf, Hout + (int64_t)v0 * 200, norm + v0, nv, HAS_LOOP, tid, kTileWarps * 32);
   for (int i = tid; i < NODES * 200; i += kTileWarps * 32) (&agg[0][0])[i] = 0.f;
   if (tid <= nv) s_rp[tid] = __ldg(row_ptr + v0 + tid);
   __syncthreads();
   tile_accumulate<false, INDEXED, false>(agg, s_rp, nv, H, h_index, W, col_src, col_type, nullptr);
+  cp_async_wait_all();
   __syncthreads();
-  // epilogue: nv rows x 100 float2, coalesced
+  // epilogue: nv rows x 100 float2, coalesced; self-loop rows and norms were prefetched into shared memory
   for (int i = tid; i < nv * 100; i += kTileWarps * 32) {
     const int r = i / 100, c = (i % 100) * 2;
     const int v = v0 + r;
@@ -44,11 +48,11 @@ rgcn_gather_d200_kernel(const float* __restrict__ H, const int32_t* __restrict__
       const int64_t hr = INDEXED ? (int64_t)__ldg(h_index + v) : v;
       a = *reinterpret_cast<const float2*>(H + hr * 200 + c);
     }
-    const float nvv = __ldg(norm + v);
+    const float nvv = normbuf[r];
     float* op = Hout + (int64_t)v * 200 + c;
     float2 o = make_float2(a.x * nvv, a.y * nvv);
     if (HAS_LOOP) {
-      const float2 l = *reinterpret_cast<const float2*>(op);
+      const float2 l = *reinterpret_cast<const float2*>(&loopbuf[r][c]);
       o.x += l.x; o.y += l.y;
     }
     if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
@@ -70,7 +74,9 @@ rgcn_gather_comp_kernel(const float* __restrict__ H, const int32_t* __restrict__
   float* win = csm;
   float* wc = win + kWinRows * 200;
   float(*agg)[kTileNodes][200] = reinterpret_cast<float(*)[kTileNodes][200]>(wc + kHotRel * 400);
-  int* s_rp_all = reinterpret_cast<int*>(wc + kHotRel * 400 + kCompGroups * kTileNodes * 200);
+  float(*loopb)[kTileNodes][200] = agg + kCompGroups;
+  float* normb_all = reinterpret_cast<float*>(loopb + kCompGroups);
+  int* s_rp_all = reinterpret_cast<int*>(normb_all + kCompGroups * kTileNodes);
   const int tid = threadIdx.x;
   const int comp = comp_order != nullptr ? __ldg(comp_order + blockIdx.x) : blockIdx.x;
   const int v_lo = __ldg(comp_ptr + comp), v_hi = __ldg(comp_ptr + comp + 1);
@@ -84,21 +90,24 @@ rgcn_gather_comp_kernel(const float* __restrict__ H, const int32_t* __restrict__
   for (int tile = group; tile < n_tiles; tile += kCompGroups) {
     const int v0 = v_lo + tile * kTileNodes;
     const int nv = min(kTileNodes, v_hi - v0);
+    tile_prefetch_epilogue(loopb[group], normb_all + group * kTileNodes, Hout + (int64_t)v0 * 200, norm + v0, nv,
+                           HAS_LOOP, gtid, kTileWarps * 32);
     for (int i = gtid; i < kTileNodes * 200; i += kTileWarps * 32) (&my_agg[0][0])[i] = 0.f;
     if (gtid <= nv) s_rp[gtid] = __ldg(row_ptr + v0 + gtid);
     group_barrier(group);
     comp_tile_accumulate<false, INDEXED, false>(my_agg, s_rp, nv, gwarp, H, h_index, W, col_src, col_type, nullptr,
                                                 win, v_lo, win_n, wc, n_hot > 0 ? rel_slot : nullptr);
+    cp_async_wait_all();
     group_barrier(group);
     for (int i = gtid; i < nv * 100; i += kTileWarps * 32) {
       const int r = i / 100, c = (i % 100) * 2;
       const int v = v0 + r;
       const float2 a = *reinterpret_cast<const float2*>(&my_agg[r][c]);
-      const float nvv = __ldg(norm + v);
+      const float nvv = normb_all[group * kTileNodes + r];
       float* op = Hout + (int64_t)v * 200 + c;
       float2 o = make_float2(a.x * nvv, a.y * nvv);
       if (HAS_LOOP) {
-        const float2 l = *reinterpret_cast<const float2*>(op);
+        const float2 l = *reinterpret_cast<const float2*>(&loopb[group][r][c]);
         o.x += l.x; o.y += l.y;
       }
       if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
@@ -142,8 +151,8 @@ __global__ void rgcn_gather_generic_kernel(const float* __restrict__ H, const in
 
 }  // namespace
 
-// experiment knob (RENET_GATHER_VARIANT / renet_set_gather_variant): 0 = 16 nodes per CTA, 1 = 16 nodes + at
-// least 4 CTAs/SM, 2 = 32 nodes, 3 = 32 nodes + 4 CTAs/SM, 4 = prefer the component-resident kernel
+// experiment knob (RENET_GATHER_VARIANT / renet_set_gather_variant): 0 = at least 3 CTAs/SM (default),
+// 1 = at least 4 CTAs/SM (64 registers)
 static int g_gather_variant = -1;
 int gather_variant() {
   if (g_gather_variant < 0) {
@@ -170,15 +179,12 @@ int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, c
   if (fast) {
     const unsigned block = kTileWarps * 32;
     const int variant = gather_variant();
-    const int nodes = (variant == 2 || variant == 3) ? 32 : 16;
-    const unsigned grid = (unsigned)((N + nodes - 1) / nodes);
+    const unsigned grid = (unsigned)((N + kTileNodes - 1) / kTileNodes);
 #define RENET_LAUNCH_GATHER(R, L, I)                                                                            \
-  switch (variant) {                                                                                            \
-    case 1: rgcn_gather_d200_kernel<R, L, I, 16, 4><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough); break; \
-    case 2: rgcn_gather_d200_kernel<R, L, I, 32, 3><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough); break; \
-    case 3: rgcn_gather_d200_kernel<R, L, I, 32, 4><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough); break; \
-    default: rgcn_gather_d200_kernel<R, L, I, 16, 3><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough); break; \
-  }
+  if (variant == 1)                                                                                             \
+    rgcn_gather_d200_kernel<R, L, I, kTileNodes, 4><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough); \
+  else                                                                                                          \
+    rgcn_gather_d200_kernel<R, L, I, kTileNodes, 3><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough)
     const int key = (relu ? 4 : 0) | (has_loop ? 2 : 0) | (h_index ? 1 : 0);
     switch (key) {
       case 0: RENET_LAUNCH_GATHER(false, false, false); break;

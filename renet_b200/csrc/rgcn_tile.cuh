@@ -28,6 +28,26 @@ __device__ __forceinline__ float2 ldg_f2_stream(const float* p) {
   return r;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Prefetch what the epilogue needs (the tile's self-loop rows and norms) into shared memory with cp.async
+// BEFORE the edge loop, so the epilogue has no exposed global latency.  nthreads threads, local id t.
+__device__ __forceinline__ void tile_prefetch_epilogue(float (*loopbuf)[200], float* normbuf,
+                                                       const float* __restrict__ loop_rows /* Hout + v0*200 */,
+                                                       const float* __restrict__ norm_v0, int nv, bool has_loop,
+                                                       int t, int nthreads) {
+  if (has_loop)
+    for (int i = t; i < nv * 50; i += nthreads) cp_async16(&loopbuf[0][0] + i * 4, loop_rows + i * 4);
+  if (t < nv) normbuf[t] = __ldg(norm_v0 + t);
+  cp_async_commit();
+}
+
 struct EdgeData {
   float2 h[4];
   float4 w[4];
