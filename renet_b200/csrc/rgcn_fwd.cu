@@ -19,8 +19,10 @@
 namespace renet {
 namespace {
 
-template <bool RELU, bool HAS_LOOP, bool INDEXED, int NODES = kTileNodes, int MINB = 1>
-__global__ void __launch_bounds__(kTileWarps * 32, MINB)
+// VARIANT 0: one tile per CTA, source rows streamed past L1.  1: source rows allocate in L1.  2: persistent
+// CTAs, each walking a contiguous range of tiles (same component -> source rows re-used from L1).
+template <bool RELU, bool HAS_LOOP, bool INDEXED, int NODES = kTileNodes, int VARIANT = 0>
+__global__ void __launch_bounds__(kTileWarps * 32, 3)
 rgcn_gather_d200_kernel(const float* __restrict__ H, const int32_t* __restrict__ h_index,
                         const float* __restrict__ W, const int32_t* __restrict__ row_ptr,
                         const int32_t* __restrict__ col_src, const int32_t* __restrict__ col_type,
@@ -30,13 +32,22 @@ rgcn_gather_d200_kernel(const float* __restrict__ H, const int32_t* __restrict__
   __shared__ float normbuf[NODES];
   __shared__ int s_rp[NODES + 1];
   const int tid = threadIdx.x;
-  const int v0 = blockIdx.x * NODES;
+  const int n_tiles = (N + NODES - 1) / NODES;
+  int tile_lo = blockIdx.x, tile_hi = blockIdx.x + 1;
+  if (VARIANT == 2) {
+    const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
+    tile_lo = blockIdx.x * per;
+    tile_hi = min(n_tiles, tile_lo + per);
+  }
+  for (int tile = tile_lo; tile < tile_hi; ++tile) {
+  if (tile > tile_lo) __syncthreads();
+  const int v0 = tile * NODES;
   const int nv = min(NODES, N - v0);
   tile_prefetch_epilogue(loopbuf, normbuf, Hout + (int64_t)v0 * 200, norm + v0, nv, HAS_LOOP, tid, kTileWarps * 32);
   for (int i = tid; i < NODES * 200; i += kTileWarps * 32) (&agg[0][0])[i] = 0.f;
   if (tid <= nv) s_rp[tid] = __ldg(row_ptr + v0 + tid);
   __syncthreads();
-  tile_accumulate<false, INDEXED, false>(agg, s_rp, nv, H, h_index, W, col_src, col_type, nullptr);
+  tile_accumulate<false, INDEXED, false, VARIANT == 0>(agg, s_rp, nv, H, h_index, W, col_src, col_type, nullptr);
   cp_async_wait_all();
   __syncthreads();
   // epilogue: nv rows x 100 float2, coalesced; self-loop rows and norms were prefetched into shared memory
@@ -57,6 +68,7 @@ rgcn_gather_d200_kernel(const float* __restrict__ H, const int32_t* __restrict__
     }
     if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
     *reinterpret_cast<float2*>(op) = o;
+  }
   }
 }
 
@@ -179,12 +191,15 @@ int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, c
   if (fast) {
     const unsigned block = kTileWarps * 32;
     const int variant = gather_variant();
-    const unsigned grid = (unsigned)((N + kTileNodes - 1) / kTileNodes);
+    const unsigned n_tiles = (unsigned)((N + kTileNodes - 1) / kTileNodes);
+    const unsigned grid = variant == 2 ? min(n_tiles, (unsigned)(kNumSMs * 3)) : n_tiles;
 #define RENET_LAUNCH_GATHER(R, L, I)                                                                            \
   if (variant == 1)                                                                                             \
-    rgcn_gather_d200_kernel<R, L, I, kTileNodes, 4><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough); \
+    rgcn_gather_d200_kernel<R, L, I, kTileNodes, 1><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough); \
+  else if (variant == 2)                                                                                        \
+    rgcn_gather_d200_kernel<R, L, I, kTileNodes, 2><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough); \
   else                                                                                                          \
-    rgcn_gather_d200_kernel<R, L, I, kTileNodes, 3><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough)
+    rgcn_gather_d200_kernel<R, L, I, kTileNodes, 0><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough)
     const int key = (relu ? 4 : 0) | (has_loop ? 2 : 0) | (h_index ? 1 : 0);
     switch (key) {
       case 0: RENET_LAUNCH_GATHER(false, false, false); break;

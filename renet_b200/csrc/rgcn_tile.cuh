@@ -53,13 +53,14 @@ struct EdgeData {
   float4 w[4];
 };
 
+template <bool STREAM_X = true>
 __device__ __forceinline__ void load_edge(EdgeData& d, const float* __restrict__ X, const float* __restrict__ W,
                                           int s, int t, int lane) {
   const float* xp = X + (int64_t)s * 200 + 2 * lane;
   const float* wp = W + (int64_t)t * 400 + 4 * lane;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    d.h[k] = ldg_f2_stream(xp + 50 * k);
+    d.h[k] = STREAM_X ? ldg_f2_stream(xp + 50 * k) : __ldg(reinterpret_cast<const float2*>(xp + 50 * k));
     d.w[k] = ldg_f4(wp + 100 * k);
   }
 }
@@ -83,7 +84,7 @@ __device__ __forceinline__ void fma_edge(float (&acc)[8], const EdgeData& d, flo
 // Accumulate the tile's messages into `agg` (shared, [kTileNodes][200], zeroed by this function).
 // s_rp: shared copy of row_ptr[v0 .. v0+nv].  EDGE_SCALE: multiply each message by scale[col_a[e]]
 // (backward: norm of the edge's destination).
-template <bool TRANSPOSE, bool INDEXED, bool EDGE_SCALE, bool SMEM_IDX = false>
+template <bool TRANSPOSE, bool INDEXED, bool EDGE_SCALE, bool STREAM_X = true>
 __device__ __forceinline__ void tile_accumulate(float (*agg)[200], const int* s_rp, int nv,
                                                 const float* __restrict__ X, const int32_t* __restrict__ x_index,
                                                 const float* __restrict__ W, const int32_t* __restrict__ col_a,
@@ -139,8 +140,8 @@ __device__ __forceinline__ void tile_accumulate(float (*agg)[200], const int* s_
       const float cb = EDGE_SCALE ? __shfl_sync(0xffffffffu, my_sc, jb) : 1.f;
       EdgeData da, db;
       if (active) {             // both edges' 16 loads are issued before any use
-        load_edge(da, X, W, sa, ta, lane);
-        load_edge(db, X, W, sb, tb, lane);
+        load_edge<STREAM_X>(da, X, W, sa, ta, lane);
+        load_edge<STREAM_X>(db, X, W, sb, tb, lane);
       }
       advance(base + j);
       if (active) fma_edge<TRANSPOSE>(acc, da, ca);

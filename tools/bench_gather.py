@@ -56,6 +56,6 @@ def run(kind, variant, layer1):
 
 
 for layer1 in (True, False):
-    for v in (0, 1):
+    for v in (0, 1, 2):
         run('tile', v, layer1)
     run('comp', 0, layer1)
