@@ -49,6 +49,12 @@ int renet_get_gemm_engine(void);
 /* Tuning knob for renet_rgcn_gather's d=200 kernel (tile size / occupancy variants, see rgcn_fwd.cu);
  * results are identical across variants.  Returns the previous value. */
 int renet_set_gather_variant(int variant);
+/* Optional caller-owned DEVICE scratch buffer (128-byte aligned) the tensor-core GEMM engine uses for the packed
+ * (hi/lo split, K-major, 128-byte-swizzled) copy of the B operand, so that GEMM CTAs can fetch it with TMA bulk
+ * copies.  Needs ceil(N/200)*ceil(K/32)*53248 bytes per GEMM (W_loop: 373 KB; GRU input projection: 2.2 MB); without
+ * it (or if it is too small) the engine stages B itself.  The buffer is shared by all GEMMs: issue them on ONE
+ * stream.  Pass NULL/0 to unregister.  The library never frees it. */
+int renet_set_scratch(void* device_ptr, int64_t bytes);
 
 /* ------------------------------------------------------------------------------------------------
  * Graph preprocessing.  Replaces what DGL does inside g.update_all (RGCN.py:91) to find the

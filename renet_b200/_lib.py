@@ -21,6 +21,7 @@ SIGNATURES = {
     'renet_set_gemm_engine': (ctypes.c_int, [ctypes.c_int]),
     'renet_get_gemm_engine': (ctypes.c_int, []),
     'renet_set_gather_variant': (ctypes.c_int, [ctypes.c_int]),
+    'renet_set_scratch': (ctypes.c_int, [_vp, _i64]),
     'renet_csr_workspace_bytes': (_i64, [_i64, _i64]),
     'renet_build_csr': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     'renet_rgcn_block_fwd': (ctypes.c_int, [_vp] * 9 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
@@ -71,6 +72,7 @@ def ptr(t):
 
 
 def stream():
+    ensure_scratch(torch.cuda.current_device())
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -79,6 +81,20 @@ def require_cuda(*tensors):
         if t is not None and not t.is_cuda:
             raise RuntimeError('renet_b200: the hot path runs on CUDA only (got a %s tensor); '
                                'there is no CPU fallback' % t.device)
+
+
+_scratch = {}
+
+
+def ensure_scratch(device, nbytes=16 << 20):
+    """Register a per-process device scratch buffer for the tensor-core GEMM engine (packed B operand)."""
+    key = str(device)
+    if key not in _scratch:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=torch.device('cuda', device) if isinstance(device, int) else device)
+        check(lib().renet_set_scratch(ctypes.c_void_p(buf.data_ptr()), nbytes), 'renet_set_scratch')
+        _scratch.clear()              # one registered buffer at a time (single device per process)
+        _scratch[key] = buf
+    return _scratch[key]
 
 
 def launch_count():

@@ -269,17 +269,256 @@ umma_gemm_nn_kernel(const float* __restrict__ A, const int32_t* __restrict__ a_i
   }
 }
 
+
+// ======================================================================================================
+// v2: pre-packed B + TMA bulk copies + 128-byte swizzle
+//
+// Profiling v1 showed the tile time dominated by operand staging, not by the MMAs: every CTA re-transposed and
+// re-split the same B (W_loop / GRU weights), and the no-swizzle layout forced row-strided A loads (16 useful
+// bytes per 128-byte line with almost no L1 left beside 215 KB of shared memory).  v2:
+//   * B is packed ONCE per GEMM by umma_pack_b_kernel into the exact shared-memory image (hi and lo planes,
+//     K-major, SWIZZLE_128B, one 53 KB block per (column tile, 32-wide K chunk)); the GEMM CTAs fetch a block
+//     with a single cp.async.bulk (TMA) that completes on the stage's mbarrier;
+//   * A is staged by the threads with fully coalesced 128-byte row segments and conflict-free swizzled
+//     16-byte stores (chunk j of row r lands at chunk j ^ (r % 8));
+//   * K is processed in chunks of 32 (one swizzle atom): 4 MMA k-steps x 3 split products per chunk.
+// ======================================================================================================
+constexpr int P_BK = 32;
+constexpr int P_A_BYTES = UM * 128;                  // 16384
+constexpr int P_B_BYTES = UNP * 128;                 // 26624
+constexpr int P_B_CHUNK = 2 * P_B_BYTES;             // hi + lo planes of one (tile, chunk)
+constexpr int P_STAGE = 2 * P_A_BYTES + P_B_CHUNK;   // 86016
+constexpr int P_STAGES = 2;
+constexpr int P_SMEM = P_STAGES * P_STAGE + 1024 + 64;
+
+__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk16) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk16 ^ (row & 7)) << 4));
+}
+// K-major SWIZZLE_128B descriptor: SBO = 1024 B (8 rows x 128 B), LBO field = 1, version 1, layout type 2
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Bp[(nt * n_chunks + kc)] = {hi plane, lo plane} of B[kc*32 .. +31][nt*200 .. +207] (zero padded)
+__global__ void __launch_bounds__(256)
+umma_pack_b_kernel(const float* __restrict__ B, int64_t ldb, int N, int K, uint8_t* __restrict__ Bp, int n_chunks) {
+  const int nt = blockIdx.x, kc = blockIdx.y;
+  const int n0 = nt * UN, k0 = kc * P_BK;
+  const int tile_n = min(UN, N - n0);
+  uint8_t* dst = Bp + (size_t)(nt * n_chunks + kc) * P_B_CHUNK;
+  for (int task = threadIdx.x; task < UNP * 8; task += 256) {
+    const int j = task / UNP, n = task % UNP;      // consecutive threads -> consecutive n (coalesced reads)
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + 4 * j + i;
+      v[i] = (n < tile_n && k < K) ? __ldg(B + (int64_t)k * ldb + n0 + n) : 0.f;
+    }
+    float4 hi, lo;
+    split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+    const uint32_t off = sw128_offset(n, j);
+    *reinterpret_cast<float4*>(dst + off) = hi;
+    *reinterpret_cast<float4*>(dst + P_B_BYTES + off) = lo;
+  }
+}
+
+template <bool INDEXED>
+__global__ void __launch_bounds__(UTHREADS, 1)
+umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__ a_index, int64_t lda,
+                        const uint8_t* __restrict__ Bp, float* __restrict__ C, int64_t ldc,
+                        const float* __restrict__ bias, int64_t M, int N, int K, int n_chunks, int accumulate) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);     // swizzle atoms need 1024-byte alignment
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * UM;
+  const int nt = blockIdx.y;
+  const int n0 = nt * UN;
+  const int tile_n = min(UN, N - n0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_STAGES * P_STAGE);   // [0,1] B landed, [2,3] stage free, [4] done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P_STAGES * P_STAGE + 48);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar0 = smem_u32(bars);
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) mbar_init(bar0 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = make_idesc();
+
+  // A tasks: 128 rows x 8 sixteen-byte chunks = 1024 -> 4 per thread; 8 consecutive lanes read one 128-byte row segment
+  const float* a_rows[4];
+  uint32_t a_off[4];
+  int a_k[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int task = tid + t * UTHREADS;
+    const int r = task >> 3, j = task & 7;
+    const int64_t gr = row0 + r;
+    a_rows[t] = nullptr;
+    if (gr < M) {
+      const int64_t rr = INDEXED ? (int64_t)__ldg(a_index + gr) : gr;
+      a_rows[t] = A + rr * lda;
+    }
+    a_off[t] = sw128_offset(r, j);
+    a_k[t] = 4 * j;
+  }
+  const uint8_t* bp_tile = Bp + (size_t)nt * n_chunks * P_B_CHUNK;
+
+  for (int c = 0; c < n_chunks; ++c) {
+    const int st = c % P_STAGES;
+    uint8_t* sA_hi = smem + st * P_STAGE;
+    uint8_t* sA_lo = sA_hi + P_A_BYTES;
+    if (c >= P_STAGES) mbar_wait(bar0 + 16 + 8 * st, ((c / P_STAGES) - 1) & 1);   // MMAs of chunk c-2 have read this stage
+    if (tid == 0) {   // TMA: one bulk copy brings the packed B block (hi + lo planes), completing on the stage barrier
+      const uint32_t full = bar0 + 8 * st;
+      const uint32_t dstB = smem_base + st * P_STAGE + 2 * P_A_BYTES;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)P_B_CHUNK) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dstB),
+                   "l"(bp_tile + (size_t)c * P_B_CHUNK), "r"((uint32_t)P_B_CHUNK), "r"(full)
+                   : "memory");
+    }
+    const int k0 = c * P_BK;
+    float4 v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a_rows[t] != nullptr && k0 + a_k[t] < K) v[t] = ldg_f4(a_rows[t] + k0 + a_k[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float4 hi, lo;
+      split4(v[t], hi, lo);
+      *reinterpret_cast<float4*>(sA_hi + a_off[t]) = hi;
+      *reinterpret_cast<float4*>(sA_lo + a_off[t]) = lo;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait(bar0 + 8 * st, (c / P_STAGES) & 1);          // B block landed
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = smem_base + st * P_STAGE, a_lo = a_hi + P_A_BYTES;
+      const uint32_t b_hi = a_lo + P_A_BYTES, b_lo = b_hi + P_B_BYTES;
+#pragma unroll
+      for (int ks = 0; ks < P_BK / 8; ++ks) {
+        const uint32_t ko = ks * 32;                         // 8 fp32 = 32 bytes along the swizzled row
+        const uint64_t dAh = make_desc_sw128(a_hi + ko), dAl = make_desc_sw128(a_lo + ko);
+        const uint64_t dBh = make_desc_sw128(b_hi + ko), dBl = make_desc_sw128(b_lo + ko);
+        umma_tf32(tmem_base, dAh, dBh, idesc, (c | ks) != 0);
+        umma_tf32(tmem_base, dAl, dBh, idesc, 1);
+        umma_tf32(tmem_base, dAh, dBl, idesc, 1);
+      }
+      umma_commit(bar0 + 16 + 8 * st);
+      if (c == n_chunks - 1) umma_commit(bar0 + 32);
+    }
+  }
+
+  mbar_wait(bar0 + 32, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane;
+    const int64_t gr = row0 + r;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int cc = half * 104; cc < half * 104 + 104; cc += 8) {
+      uint32_t v8[8];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(v8[0]), "=r"(v8[1]), "=r"(v8[2]), "=r"(v8[3]), "=r"(v8[4]), "=r"(v8[5]), "=r"(v8[6]), "=r"(v8[7])
+                   : "r"(taddr + (uint32_t)cc));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (gr < M && cc < tile_n) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v8[i]);
+        float* cp = C + gr * ldc + n0 + cc;
+        if (bias != nullptr) {
+          const float4 b0 = ldg_f4(bias + n0 + cc), b1 = ldg_f4(bias + n0 + cc + 4);
+          o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+          o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+        }
+        if (accumulate) {
+          const float4 c0 = *reinterpret_cast<const float4*>(cp), c1 = *reinterpret_cast<const float4*>(cp + 4);
+          o[0] += c0.x; o[1] += c0.y; o[2] += c0.z; o[3] += c0.w;
+          o[4] += c1.x; o[5] += c1.y; o[6] += c1.z; o[7] += c1.w;
+        }
+        st_f4(cp, make_float4(o[0], o[1], o[2], o[3]));
+        st_f4(cp + 4, make_float4(o[4], o[5], o[6], o[7]));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
 }  // namespace
 
 // Returns 1 if the shape was taken by the tensor-core path (launch enqueued), 0 if the caller should
 // fall back to the FFMA kernel, negative on error.
+static uint8_t* g_scratch = nullptr;
+static int64_t g_scratch_bytes = 0;
+void set_scratch(void* p, int64_t bytes) { g_scratch = (uint8_t*)p; g_scratch_bytes = p ? bytes : 0; }
+
 int umma_gemm_nn_try(const float* A, const int32_t* a_index, int64_t lda, const float* B, int64_t ldb, float* C,
                      int64_t ldc, const float* bias, int64_t M, int32_t N, int32_t K, bool accumulate,
                      cudaStream_t stream) {
+  const bool aligned = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C) |
+                         reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
+  // ---- packed path (v2): needs the registered scratch buffer for the packed copy of B ------------------------
+  {
+    const int n_tiles = (N + UN - 1) / UN, n_chunks = (K + P_BK - 1) / P_BK;
+    const int64_t need = (int64_t)n_tiles * n_chunks * P_B_CHUNK;
+    const bool ok2 = aligned && (K % 4 == 0) && (N % 8 == 0) && (lda % 4 == 0) && (ldc % 4 == 0) && M >= 64 &&
+                     g_scratch != nullptr && need <= g_scratch_bytes &&
+                     (reinterpret_cast<uintptr_t>(g_scratch) & 127) == 0;
+    if (ok2) {
+      static bool attr2 = false;
+      if (!attr2) {
+        cudaError_t e1 = cudaFuncSetAttribute(umma_gemm_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
+        cudaError_t e2 = cudaFuncSetAttribute(umma_gemm_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+          set_error("cudaFuncSetAttribute(umma_gemm_packed_kernel) failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+          return RENET_ERR_CUDA;
+        }
+        attr2 = true;
+      }
+      umma_pack_b_kernel<<<dim3(n_tiles, n_chunks), 256, 0, stream>>>(B, ldb, N, K, g_scratch, n_chunks);
+      dim3 grid((unsigned)((M + UM - 1) / UM), (unsigned)n_tiles);
+      if (a_index)
+        umma_gemm_packed_kernel<true><<<grid, UTHREADS, P_SMEM, stream>>>(A, a_index, lda, g_scratch, C, ldc, bias, M, N, K, n_chunks, accumulate);
+      else
+        umma_gemm_packed_kernel<false><<<grid, UTHREADS, P_SMEM, stream>>>(A, a_index, lda, g_scratch, C, ldc, bias, M, N, K, n_chunks, accumulate);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) {
+        set_error("launch of umma_gemm_packed_kernel failed: %s", cudaGetErrorString(e));
+        return RENET_ERR_CUDA;
+      }
+      count_launch(2);
+      return 1;
+    }
+  }
   const bool ok = (K % UKC == 0) && K >= UKC && (N % 8 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) &&
-                  M >= 64 &&
-                  ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C) |
-                    reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
+                  M >= 64 && aligned;
   if (!ok) return 0;
   static bool attr_set = false;
   if (!attr_set) {

@@ -54,4 +54,13 @@ for eng, name in ((0, 'ffma'), (1, 'umma')):
         L.renet_selfloop_gemm(_lib.ptr(A), _lib.ptr(idx), _lib.ptr(B), _lib.ptr(out), 34483, 200, 200, _lib.stream())
     b.record(); torch.cuda.synchronize()
     print('selfloop GEMM 34483x200x200 %s: %.1f us' % (name, a.elapsed_time(b) / 20 * 1e3))
+# engine 1 without scratch = v1 (self-staged B); with scratch = v2 (packed B + TMA)
+L.renet_set_scratch(None, 0)
+A = torch.randn(5000, 200, device=dev); B = torch.randn(200, 200, device=dev) * 0.1
+ref = A.double() @ B.double()
+L.renet_set_gemm_engine(1)
+v1 = gemm(A, None, B, 5000)
+e1 = (v1.double() - ref).abs().max().item() / ref.abs().max().item()
+print('v1 (no scratch) rel err %.2e' % e1)
+assert e1 < 2e-5
 print('UMMA_OK worst %.2e' % worst)
