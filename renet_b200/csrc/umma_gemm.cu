@@ -381,6 +381,16 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
   }
   const uint8_t* bp_tile = Bp + (size_t)nt * n_chunks * P_B_CHUNK;
 
+  float4 vnext[4];
+  auto load_a = [&](int c) {
+    const int k0 = c * P_BK;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      vnext[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a_rows[t] != nullptr && k0 + a_k[t] < K) vnext[t] = ldg_f4(a_rows[t] + k0 + a_k[t]);
+    }
+  };
+  load_a(0);
   for (int c = 0; c < n_chunks; ++c) {
     const int st = c % P_STAGES;
     uint8_t* sA_hi = smem + st * P_STAGE;
@@ -394,13 +404,10 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
                    "l"(bp_tile + (size_t)c * P_B_CHUNK), "r"((uint32_t)P_B_CHUNK), "r"(full)
                    : "memory");
     }
-    const int k0 = c * P_BK;
     float4 v[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a_rows[t] != nullptr && k0 + a_k[t] < K) v[t] = ldg_f4(a_rows[t] + k0 + a_k[t]);
-    }
+    for (int t = 0; t < 4; ++t) v[t] = vnext[t];
+    if (c + 1 < n_chunks) load_a(c + 1);          // next chunk's global loads are in flight during this chunk's sync/MMA
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       float4 hi, lo;
@@ -433,17 +440,12 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
   mbar_wait(bar0 + 32, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   {
+    // thread = accumulator row; warps 0-3 take columns [0,104), warps 4-7 [104,208): 3 x (32 columns) + 1 x 8
     const int q = warp & 3, half = warp >> 2;
     const int r = q * 32 + lane;
     const int64_t gr = row0 + r;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-    for (int cc = half * 104; cc < half * 104 + 104; cc += 8) {
-      uint32_t v8[8];
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                   : "=r"(v8[0]), "=r"(v8[1]), "=r"(v8[2]), "=r"(v8[3]), "=r"(v8[4]), "=r"(v8[5]), "=r"(v8[6]), "=r"(v8[7])
-                   : "r"(taddr + (uint32_t)cc));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    auto emit8 = [&](const uint32_t* v8, int cc) {
       if (gr < M && cc < tile_n) {
         float o[8];
 #pragma unroll
@@ -462,6 +464,32 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
         st_f4(cp, make_float4(o[0], o[1], o[2], o[3]));
         st_f4(cp + 4, make_float4(o[4], o[5], o[6], o[7]));
       }
+    };
+    const int cbase = half * 104;
+#pragma unroll 1
+    for (int blk = 0; blk < 3; ++blk) {
+      uint32_t v[32];
+      const int cc = cbase + blk * 32;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr + (uint32_t)cc));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8) emit8(v + 8 * g8, cc + 8 * g8);
+    }
+    {
+      uint32_t v8[8];
+      const int cc = cbase + 96;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(v8[0]), "=r"(v8[1]), "=r"(v8[2]), "=r"(v8[3]), "=r"(v8[4]), "=r"(v8[5]), "=r"(v8[6]), "=r"(v8[7])
+                   : "r"(taddr + (uint32_t)cc));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      emit8(v8, cc);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
