@@ -287,9 +287,7 @@ constexpr int P_BK = 32;
 constexpr int P_A_BYTES = UM * 128;                  // 16384
 constexpr int P_B_BYTES = UNP * 128;                 // 26624
 constexpr int P_B_CHUNK = 2 * P_B_BYTES;             // hi + lo planes of one (tile, chunk)
-constexpr int P_STAGE = 2 * P_A_BYTES + P_B_CHUNK;   // 86016
-constexpr int P_STAGES = 2;
-constexpr int P_SMEM = P_STAGES * P_STAGE + 1024 + 64;
+constexpr int P_SMEM = 4 * P_A_BYTES + 2 * P_B_CHUNK + 1024 + 128;   // two tiles' A (hi,lo) + two B stages
 
 __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk16) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk16 ^ (row & 7)) << 4));
@@ -312,7 +310,7 @@ umma_pack_b_kernel(const float* __restrict__ B, int64_t ldb, int N, int K, uint8
   const int n0 = nt * UN, k0 = kc * P_BK;
   const int tile_n = min(UN, N - n0);
   uint8_t* dst = Bp + (size_t)(nt * n_chunks + kc) * P_B_CHUNK;
-  for (int task = threadIdx.x; task < UNP * 8; task += 256) {
+  for (int task = blockIdx.z * 256 + threadIdx.x; task < UNP * 8; task += 256 * gridDim.z) {
     const int j = task / UNP, n = task % UNP;      // consecutive threads -> consecutive n (coalesced reads)
     float v[4];
 #pragma unroll
@@ -328,31 +326,36 @@ umma_pack_b_kernel(const float* __restrict__ B, int64_t ldb, int N, int K, uint8
   }
 }
 
+// One CTA = a PAIR of 128-row tiles sharing every B block: the packed B chunk (53 KB) is fetched once per pair,
+// the two tiles' A buffers ping-pong (tile 1's chunk is staged while tile 0's MMAs run and vice versa), and the
+// two accumulators live side by side in TMEM (2 x 256 columns).
 template <bool INDEXED>
 __global__ void __launch_bounds__(UTHREADS, 1)
 umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__ a_index, int64_t lda,
                         const uint8_t* __restrict__ Bp, float* __restrict__ C, int64_t ldc,
-                        const float* __restrict__ bias, int64_t M, int N, int K, int n_chunks, int accumulate) {
+                        const float* __restrict__ bias, int64_t M, int N, int K, int n_chunks, int accumulate, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);     // swizzle atoms need 1024-byte alignment
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t row0 = (int64_t)blockIdx.x * UM;
+  const int64_t row_base = (int64_t)blockIdx.x * (2 * UM);
   const int nt = blockIdx.y;
   const int n0 = nt * UN;
   const int tile_n = min(UN, N - n0);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_STAGES * P_STAGE);   // [0,1] B landed, [2,3] stage free, [4] done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P_STAGES * P_STAGE + 48);
+  // smem: A[2 tiles][hi,lo] (4 x 16 KB), B[2 stages][hi,lo] (2 x 53 KB), barriers
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 4 * P_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * P_B_CHUNK);   // [0,1] B landed, [2,3] B free, [4,5] A_t free, [6] done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar0 = smem_u32(bars);
   if (tid == 0) {
-    for (int i = 0; i < 5; ++i) mbar_init(bar0 + 8 * i, 1);
+    for (int i = 0; i < 7; ++i) mbar_init(bar0 + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(TMEM_COLS)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -362,140 +365,158 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t idesc = make_idesc();
 
-  // A tasks: 128 rows x 8 sixteen-byte chunks = 1024 -> 4 per thread; 8 consecutive lanes read one 128-byte row segment
-  const float* a_rows[4];
+  // A tasks per tile: 128 rows x 8 sixteen-byte chunks = 1024 -> 4 per thread; 8 consecutive lanes read one
+  // 128-byte row segment (coalesced), and write it to 8 distinct swizzled chunks (conflict-free)
+  const float* a_rows[2][4];
   uint32_t a_off[4];
   int a_k[4];
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     const int task = tid + t * UTHREADS;
     const int r = task >> 3, j = task & 7;
-    const int64_t gr = row0 + r;
-    a_rows[t] = nullptr;
-    if (gr < M) {
-      const int64_t rr = INDEXED ? (int64_t)__ldg(a_index + gr) : gr;
-      a_rows[t] = A + rr * lda;
-    }
     a_off[t] = sw128_offset(r, j);
     a_k[t] = 4 * j;
+#pragma unroll
+    for (int tl = 0; tl < 2; ++tl) {
+      const int64_t gr = row_base + tl * UM + r;
+      a_rows[tl][t] = nullptr;
+      if (gr < M) {
+        const int64_t rr = INDEXED ? (int64_t)__ldg(a_index + gr) : gr;
+        a_rows[tl][t] = A + rr * lda;
+      }
+    }
   }
   const uint8_t* bp_tile = Bp + (size_t)nt * n_chunks * P_B_CHUNK;
-
   float4 vnext[4];
-  auto load_a = [&](int c) {
+  auto load_a = [&](int tl, int c) {
     const int k0 = c * P_BK;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       vnext[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a_rows[t] != nullptr && k0 + a_k[t] < K) vnext[t] = ldg_f4(a_rows[t] + k0 + a_k[t]);
+      if (a_rows[tl][t] != nullptr && k0 + a_k[t] < K) vnext[t] = ldg_f4(a_rows[tl][t] + k0 + a_k[t]);
     }
   };
-  load_a(0);
+  load_a(0, 0);
   for (int c = 0; c < n_chunks; ++c) {
-    const int st = c % P_STAGES;
-    uint8_t* sA_hi = smem + st * P_STAGE;
-    uint8_t* sA_lo = sA_hi + P_A_BYTES;
-    if (c >= P_STAGES) mbar_wait(bar0 + 16 + 8 * st, ((c / P_STAGES) - 1) & 1);   // MMAs of chunk c-2 have read this stage
-    if (tid == 0) {   // TMA: one bulk copy brings the packed B block (hi + lo planes), completing on the stage barrier
-      const uint32_t full = bar0 + 8 * st;
-      const uint32_t dstB = smem_base + st * P_STAGE + 2 * P_A_BYTES;
+    const int bs = c & 1;
+    if (tid == 0 && !(dbg & 16)) {   // TMA: one bulk copy per chunk brings the packed B block for BOTH tiles
+      if (c >= 2) mbar_wait(bar0 + 16 + 8 * bs, ((c >> 1) - 1) & 1);          // both tiles' MMAs of chunk c-2 done
+      const uint32_t full = bar0 + 8 * bs;
+      const uint32_t dstB = smem_base + 4 * P_A_BYTES + bs * P_B_CHUNK;
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)P_B_CHUNK) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dstB),
                    "l"(bp_tile + (size_t)c * P_B_CHUNK), "r"((uint32_t)P_B_CHUNK), "r"(full)
                    : "memory");
     }
-    float4 v[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) v[t] = vnext[t];
-    if (c + 1 < n_chunks) load_a(c + 1);          // next chunk's global loads are in flight during this chunk's sync/MMA
+    for (int tl = 0; tl < 2; ++tl) {
+      uint8_t* sA_hi = sA + tl * 2 * P_A_BYTES;
+      uint8_t* sA_lo = sA_hi + P_A_BYTES;
+      if (c >= 1) mbar_wait(bar0 + 32 + 8 * tl, (c - 1) & 1);                 // MMAs of (tile tl, chunk c-1) have read A_tl
+      float4 v[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float4 hi, lo;
-      split4(v[t], hi, lo);
-      *reinterpret_cast<float4*>(sA_hi + a_off[t]) = hi;
-      *reinterpret_cast<float4*>(sA_lo + a_off[t]) = lo;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      mbar_wait(bar0 + 8 * st, (c / P_STAGES) & 1);          // B block landed
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = smem_base + st * P_STAGE, a_lo = a_hi + P_A_BYTES;
-      const uint32_t b_hi = a_lo + P_A_BYTES, b_lo = b_hi + P_B_BYTES;
-#pragma unroll
-      for (int ks = 0; ks < P_BK / 8; ++ks) {
-        const uint32_t ko = ks * 32;                         // 8 fp32 = 32 bytes along the swizzled row
-        const uint64_t dAh = make_desc_sw128(a_hi + ko), dAl = make_desc_sw128(a_lo + ko);
-        const uint64_t dBh = make_desc_sw128(b_hi + ko), dBl = make_desc_sw128(b_lo + ko);
-        umma_tf32(tmem_base, dAh, dBh, idesc, (c | ks) != 0);
-        umma_tf32(tmem_base, dAl, dBh, idesc, 1);
-        umma_tf32(tmem_base, dAh, dBl, idesc, 1);
+      for (int t = 0; t < 4; ++t) v[t] = vnext[t];
+      if (!(dbg & 2)) {                                                       // next step's global loads fly during this step
+        if (tl == 0) load_a(1, c);
+        else if (c + 1 < n_chunks) load_a(0, c + 1);
       }
-      umma_commit(bar0 + 16 + 8 * st);
-      if (c == n_chunks - 1) umma_commit(bar0 + 32);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float4 hi, lo;
+        split4(v[t], hi, lo);
+        *reinterpret_cast<float4*>(sA_hi + a_off[t]) = hi;
+        *reinterpret_cast<float4*>(sA_lo + a_off[t]) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        if (tl == 0 && !(dbg & 16)) mbar_wait(bar0 + 8 * bs, (c >> 1) & 1);   // B block landed
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_base + tl * 2 * P_A_BYTES, a_lo = a_hi + P_A_BYTES;
+        const uint32_t b_hi = smem_base + 4 * P_A_BYTES + bs * P_B_CHUNK, b_lo = b_hi + P_B_BYTES;
+        const uint32_t acc = tmem_base + tl * 256;
+#pragma unroll
+        for (int ks = 0; ks < P_BK / 8; ++ks) {
+          const uint32_t ko = ks * 32;                       // 8 fp32 = 32 bytes along the swizzled row
+          const uint64_t dAh = make_desc_sw128(a_hi + ko), dAl = make_desc_sw128(a_lo + ko);
+          const uint64_t dBh = make_desc_sw128(b_hi + ko), dBl = make_desc_sw128(b_lo + ko);
+          if (dbg & 1) continue;
+          umma_tf32(acc, dAh, dBh, idesc, (c | ks) != 0);
+          umma_tf32(acc, dAl, dBh, idesc, 1);
+          umma_tf32(acc, dAh, dBl, idesc, 1);
+        }
+        umma_commit(bar0 + 32 + 8 * tl);                     // A_tl may be overwritten
+        if (tl == 1) {
+          umma_commit(bar0 + 16 + 8 * bs);                   // B stage may be overwritten
+          if (c == n_chunks - 1) umma_commit(bar0 + 48);     // both accumulators complete
+        }
+      }
     }
   }
 
-  mbar_wait(bar0 + 32, 0);
+  mbar_wait(bar0 + 48, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   {
     // thread = accumulator row; warps 0-3 take columns [0,104), warps 4-7 [104,208): 3 x (32 columns) + 1 x 8
     const int q = warp & 3, half = warp >> 2;
     const int r = q * 32 + lane;
-    const int64_t gr = row0 + r;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    auto emit8 = [&](const uint32_t* v8, int cc) {
-      if (gr < M && cc < tile_n) {
-        float o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v8[i]);
-        float* cp = C + gr * ldc + n0 + cc;
-        if (bias != nullptr) {
-          const float4 b0 = ldg_f4(bias + n0 + cc), b1 = ldg_f4(bias + n0 + cc + 4);
-          o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
-          o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
-        }
-        if (accumulate) {
-          const float4 c0 = *reinterpret_cast<const float4*>(cp), c1 = *reinterpret_cast<const float4*>(cp + 4);
-          o[0] += c0.x; o[1] += c0.y; o[2] += c0.z; o[3] += c0.w;
-          o[4] += c1.x; o[5] += c1.y; o[6] += c1.z; o[7] += c1.w;
-        }
-        st_f4(cp, make_float4(o[0], o[1], o[2], o[3]));
-        st_f4(cp + 4, make_float4(o[4], o[5], o[6], o[7]));
-      }
-    };
     const int cbase = half * 104;
 #pragma unroll 1
-    for (int blk = 0; blk < 3; ++blk) {
-      uint32_t v[32];
-      const int cc = cbase + blk * 32;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr + (uint32_t)cc));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int tl = 0; tl < 2; ++tl) {
+      const int64_t gr = row_base + tl * UM + r;
+      const uint32_t taddr = tmem_base + tl * 256 + ((uint32_t)(q * 32) << 16);
+      auto emit8 = [&](const uint32_t* v8, int cc) {
+        if (gr < M && cc < tile_n && !(dbg & 4)) {
+          float o[8];
 #pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) emit8(v + 8 * g8, cc + 8 * g8);
-    }
-    {
-      uint32_t v8[8];
-      const int cc = cbase + 96;
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                   : "=r"(v8[0]), "=r"(v8[1]), "=r"(v8[2]), "=r"(v8[3]), "=r"(v8[4]), "=r"(v8[5]), "=r"(v8[6]), "=r"(v8[7])
-                   : "r"(taddr + (uint32_t)cc));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      emit8(v8, cc);
+          for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v8[i]);
+          float* cp = C + gr * ldc + n0 + cc;
+          if (bias != nullptr) {
+            const float4 b0 = ldg_f4(bias + n0 + cc), b1 = ldg_f4(bias + n0 + cc + 4);
+            o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+            o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+          }
+          if (accumulate) {
+            const float4 c0 = *reinterpret_cast<const float4*>(cp), c1 = *reinterpret_cast<const float4*>(cp + 4);
+            o[0] += c0.x; o[1] += c0.y; o[2] += c0.z; o[3] += c0.w;
+            o[4] += c1.x; o[5] += c1.y; o[6] += c1.z; o[7] += c1.w;
+          }
+          st_f4(cp, make_float4(o[0], o[1], o[2], o[3]));
+          st_f4(cp + 4, make_float4(o[4], o[5], o[6], o[7]));
+        }
+      };
+#pragma unroll 1
+      for (int blk = 0; blk < 3; ++blk) {
+        uint32_t v[32];
+        const int cc = cbase + blk * 32;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr + (uint32_t)cc));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) emit8(v + 8 * g8, cc + 8 * g8);
+      }
+      {
+        uint32_t v8[8];
+        const int cc = cbase + 96;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v8[0]), "=r"(v8[1]), "=r"(v8[2]), "=r"(v8[3]), "=r"(v8[4]), "=r"(v8[5]), "=r"(v8[6]), "=r"(v8[7])
+                     : "r"(taddr + (uint32_t)cc));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        emit8(v8, cc);
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }
 
@@ -503,6 +524,8 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
 
 // Returns 1 if the shape was taken by the tensor-core path (launch enqueued), 0 if the caller should
 // fall back to the FFMA kernel, negative on error.
+static int g_dbg = 0;
+void set_gemm_debug(int d) { g_dbg = d; }
 static uint8_t* g_scratch = nullptr;
 static int64_t g_scratch_bytes = 0;
 void set_scratch(void* p, int64_t bytes) { g_scratch = (uint8_t*)p; g_scratch_bytes = p ? bytes : 0; }
@@ -530,12 +553,12 @@ int umma_gemm_nn_try(const float* A, const int32_t* a_index, int64_t lda, const 
         }
         attr2 = true;
       }
-      umma_pack_b_kernel<<<dim3(n_tiles, n_chunks), 256, 0, stream>>>(B, ldb, N, K, g_scratch, n_chunks);
-      dim3 grid((unsigned)((M + UM - 1) / UM), (unsigned)n_tiles);
+      if (!(g_dbg & 32)) umma_pack_b_kernel<<<dim3(n_tiles, n_chunks, 7), 256, 0, stream>>>(B, ldb, N, K, g_scratch, n_chunks);
+      dim3 grid((unsigned)((M + 2 * UM - 1) / (2 * UM)), (unsigned)n_tiles);
       if (a_index)
-        umma_gemm_packed_kernel<true><<<grid, UTHREADS, P_SMEM, stream>>>(A, a_index, lda, g_scratch, C, ldc, bias, M, N, K, n_chunks, accumulate);
+        umma_gemm_packed_kernel<true><<<grid, UTHREADS, P_SMEM, stream>>>(A, a_index, lda, g_scratch, C, ldc, bias, M, N, K, n_chunks, accumulate, g_dbg);
       else
-        umma_gemm_packed_kernel<false><<<grid, UTHREADS, P_SMEM, stream>>>(A, a_index, lda, g_scratch, C, ldc, bias, M, N, K, n_chunks, accumulate);
+        umma_gemm_packed_kernel<false><<<grid, UTHREADS, P_SMEM, stream>>>(A, a_index, lda, g_scratch, C, ldc, bias, M, N, K, n_chunks, accumulate, g_dbg);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) {
         set_error("launch of umma_gemm_packed_kernel failed: %s", cudaGetErrorString(e));
