@@ -14,6 +14,9 @@ import torch.nn.functional as F
 from . import _lib
 
 
+USE_COMPONENT_KERNEL = False
+
+
 def _buf(shape, like, dtype=torch.float32):
     return torch.empty(shape, dtype=dtype, device=like.device)
 
@@ -81,8 +84,9 @@ class _GatherFn(torch.autograd.Function):
                 ctx.mark_dirty(loop)
         d_in = H.shape[1]
         comp = getattr(g, 'comp', None)
-        if comp is not None and g.E > 0 and comp[bool(reverse)][2].numel() <= W.shape[0]:
-            # batched history graph with its component table: component-resident kernel
+        if USE_COMPONENT_KERNEL and comp is not None and g.E > 0 and comp[bool(reverse)][2].numel() <= W.shape[0]:
+            # batched history graph with its component table: component-resident kernel (experimental: slower
+            # than the tile kernel on B200 at ICEWS18 scale)
             cptr, corder, slot, hot, n_hot = comp[bool(reverse)]
             rc = L.renet_rgcn_gather_comp(_lib.ptr(H), _lib.ptr(h_index), _lib.ptr(W), _lib.ptr(g.row_ptr),
                                           _lib.ptr(g.col_src), _lib.ptr(g.col_type(reverse)), _lib.ptr(g.norm),

@@ -13,7 +13,7 @@ tail -4 gpurun_out/bench.log
 if [ "$1" != "quick" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 1 --pool 2 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launch.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:rgcn_gather_comp -s 4 -c 4 -f -o gpurun_out/prof_gather \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:rgcn_gather_d200 -s 4 -c 4 -f -o gpurun_out/prof_gather \
       python bench.py --steps 2 --warmup 1 --pool 2 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1
   ls -la gpurun_out
 fi
