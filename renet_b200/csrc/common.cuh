@@ -74,4 +74,13 @@ int sgemm_tn(const float* A, const int32_t* a_index, int64_t lda, const float* B
 int sgemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
              int64_t M, int32_t N, int32_t K, bool accumulate, cudaStream_t stream);
 
+// tcgen05 GEMM engine building blocks (umma_gemm.cu); gemm_mode() == 1 selects the engine
+int gemm_mode();
+int64_t umma_packed_bytes(int N, int K);
+bool umma_shape_ok(int N, int K);
+int umma_pack_b(const float* B, int64_t sk, int64_t sn, int N, int K, void* Bp, int tile_offset, cudaStream_t stream);
+int umma_gemm_prepacked(const float* A, const int32_t* a_index, int64_t lda, const void* Bp, float* C, int64_t ldc,
+                        const float* bias, int64_t M, int N, int K, bool accumulate, int batch, int64_t batch_a,
+                        int64_t batch_bp, int64_t batch_c, cudaStream_t stream);
+
 }  // namespace renet

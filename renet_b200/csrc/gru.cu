@@ -103,6 +103,8 @@ __global__ void pack_inputs_kernel(const float* __restrict__ H2, const int32_t* 
 
 struct GruWs {
   float *Brow, *Bent, *Brel, *Bglob, *Whh, *bih, *bhh, *GI, *PQ, *PT, *GH, *Hs;
+  float *P_row, *P_ent, *P_rel, *P_glob, *P_hh;   // tensor-core engine: weights packed for umma_gemm_prepacked
+  int64_t p_hh_bytes;
   int64_t total_floats;
 };
 
@@ -124,6 +126,13 @@ GruWs carve(float* base, int64_t S, int64_t Q, int64_t T, int h, int max_len) {
   w.PT = take(T * 6 * h);
   w.GH = take((int64_t)max_len * Q * 6 * h);   // recurrent pre-activations of every step (kept for backward)
   w.Hs = take((int64_t)(max_len + 1) * Q * 2 * h);
+  off = (off + 31) & ~int64_t(31);                       // 128-byte alignment for the TMA source blocks
+  w.P_row = take(umma_packed_bytes(6 * h, h) / 4);
+  w.P_ent = take(umma_packed_bytes(6 * h, h) / 4);
+  w.P_rel = take(umma_packed_bytes(3 * h, h) / 4);
+  w.P_glob = take(umma_packed_bytes(6 * h, h) / 4);
+  w.p_hh_bytes = umma_packed_bytes(3 * h, h);
+  w.P_hh = take(2 * w.p_hh_bytes / 4);
   w.total_floats = off;
   return w;
 }
@@ -166,6 +175,50 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
     return RENET_OK;
   };
   int rc;
+  // Tensor-core engine: weights go straight into the UMMA operand image (hi/lo planes, K-major, 128-byte swizzle),
+  // ONCE per call -- the recurrent weights are re-used by every time step -- and every GEMM is one launch; the two
+  // encoders' recurrent GEMMs are batched into a single launch per step.
+  const bool use_umma = gemm_mode() == 1 && h % 4 == 0 && (3 * h) % 200 == 0 &&
+                        (reinterpret_cast<uintptr_t>(ws_base) & 127) == 0;
+  if (use_umma) {
+    const int t3 = 3 * h / 200;   // column tiles per encoder
+    // logical B[k][n] = w[n][col_off + k]  ->  sk = 1, sn = leading dimension of w
+    if ((rc = umma_pack_b(w_ih4, 1, 4 * h, 3 * h, h, w.P_row, 0, stream))) return rc;
+    if ((rc = umma_pack_b(w_ih3, 1, 3 * h, 3 * h, h, w.P_row, t3, stream))) return rc;
+    if ((rc = umma_pack_b(w_ih4 + h, 1, 4 * h, 3 * h, h, w.P_ent, 0, stream))) return rc;
+    if ((rc = umma_pack_b(w_ih3 + h, 1, 3 * h, 3 * h, h, w.P_ent, t3, stream))) return rc;
+    if ((rc = umma_pack_b(w_ih4 + 2 * h, 1, 4 * h, 3 * h, h, w.P_rel, 0, stream))) return rc;
+    if ((rc = umma_pack_b(w_ih4 + 3 * h, 1, 4 * h, 3 * h, h, w.P_glob, 0, stream))) return rc;
+    if ((rc = umma_pack_b(w_ih3 + 2 * h, 1, 3 * h, 3 * h, h, w.P_glob, t3, stream))) return rc;
+    if ((rc = umma_pack_b(w_hh4, 1, h, 3 * h, h, w.P_hh, 0, stream))) return rc;
+    if ((rc = umma_pack_b(w_hh3, 1, h, 3 * h, h, reinterpret_cast<uint8_t*>(w.P_hh) + w.p_hh_bytes, 0, stream))) return rc;
+    concat_bias_kernel<<<(6 * h + 255) / 256, 256, 0, stream>>>(b_ih4, b_ih3, w.bih, 3 * h);
+    RENET_CHECK_LAUNCH("concat_bias_kernel");
+    concat_bias_kernel<<<(6 * h + 255) / 256, 256, 0, stream>>>(b_hh4, b_hh3, w.bhh, 3 * h);
+    RENET_CHECK_LAUNCH("concat_bias_kernel");
+    if ((rc = umma_gemm_prepacked(H2, readout, h, w.P_row, w.GI, 6 * h, nullptr, S, 6 * h, h, false, 1, 0, 0, 0, stream))) return rc;
+    if ((rc = umma_gemm_prepacked(ent, seq_s, h, w.P_ent, w.PQ, 6 * h, w.bih, Q, 6 * h, h, false, 1, 0, 0, 0, stream))) return rc;
+    if ((rc = umma_gemm_prepacked(rel, seq_r, h, w.P_rel, w.PQ, 6 * h, nullptr, Q, 3 * h, h, true, 1, 0, 0, 0, stream))) return rc;
+    if ((rc = umma_gemm_prepacked(glob, nullptr, h, w.P_glob, w.PT, 6 * h, nullptr, T, 6 * h, h, false, 1, 0, 0, 0, stream))) return rc;
+    const int64_t hs_stride_u = Q * 2 * h;
+    for (int t = 0; t < max_len; ++t) {
+      const int n_act = host_batch_sizes[t];
+      if (n_act <= 0) break;
+      const float* Hprev = (t == 0) ? nullptr : w.Hs + (int64_t)t * hs_stride_u;
+      float* Hnext = w.Hs + (int64_t)(t + 1) * hs_stride_u;
+      float* GH = w.GH + (int64_t)t * Q * 6 * h;
+      if (t > 0) {   // both encoders in one launch: batch b reads Hprev[:, b*h:(b+1)*h], writes GH[:, b*3h:(b+1)*3h]
+        if ((rc = umma_gemm_prepacked(Hprev, nullptr, 2 * h, w.P_hh, GH, 6 * h, nullptr, n_act, 3 * h, h, false, 2, h,
+                                      w.p_hh_bytes, 3 * h, stream)))
+          return rc;
+      }
+      const int total = n_act * 2 * h;
+      gru_gate_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w.GI, w.PQ, w.PT, GH, w.bhh, row_glob, seq_start, seq_len,
+                                                              Hprev, Hnext, hn4, hn3, n_act, h, t);
+      RENET_CHECK_LAUNCH("gru_gate_kernel");
+    }
+    return RENET_OK;
+  }
   // column blocks of W_ih: encoder x4 = [row | ent | rel | glob], encoder_r x3 = [row | ent | glob]
   if ((rc = pack(w_ih4, 4 * h, 0, w.Brow, 6 * h, 0))) return rc;
   if ((rc = pack(w_ih3, 3 * h, 0, w.Brow, 6 * h, 3 * h))) return rc;

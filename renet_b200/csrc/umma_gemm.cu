@@ -305,18 +305,20 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 
 // Bp[(nt * n_chunks + kc)] = {hi plane, lo plane} of B[kc*32 .. +31][nt*200 .. +207] (zero padded)
 __global__ void __launch_bounds__(256)
-umma_pack_b_kernel(const float* __restrict__ B, int64_t ldb, int N, int K, uint8_t* __restrict__ Bp, int n_chunks) {
+umma_pack_b_kernel(const float* __restrict__ B, int64_t sk, int64_t sn, int N, int K, uint8_t* __restrict__ Bp,
+                   int n_chunks, int tile_offset) {
+  // logical B[k][n] = B[k*sk + n*sn]  (row-major [K,N]: sk = ldb, sn = 1; a [N,K] weight read transposed: sk = 1, sn = ld)
   const int nt = blockIdx.x, kc = blockIdx.y;
   const int n0 = nt * UN, k0 = kc * P_BK;
   const int tile_n = min(UN, N - n0);
-  uint8_t* dst = Bp + (size_t)(nt * n_chunks + kc) * P_B_CHUNK;
+  uint8_t* dst = Bp + (size_t)((nt + tile_offset) * n_chunks + kc) * P_B_CHUNK;
   for (int task = blockIdx.z * 256 + threadIdx.x; task < UNP * 8; task += 256 * gridDim.z) {
     const int j = task / UNP, n = task % UNP;      // consecutive threads -> consecutive n (coalesced reads)
     float v[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int k = k0 + 4 * j + i;
-      v[i] = (n < tile_n && k < K) ? __ldg(B + (int64_t)k * ldb + n0 + n) : 0.f;
+      v[i] = (n < tile_n && k < K) ? __ldg(B + (int64_t)k * sk + (int64_t)(n0 + n) * sn) : 0.f;
     }
     float4 hi, lo;
     split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
@@ -333,11 +335,16 @@ template <bool INDEXED>
 __global__ void __launch_bounds__(UTHREADS, 1)
 umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__ a_index, int64_t lda,
                         const uint8_t* __restrict__ Bp, float* __restrict__ C, int64_t ldc,
-                        const float* __restrict__ bias, int64_t M, int N, int K, int n_chunks, int accumulate, int dbg) {
+                        const float* __restrict__ bias, int64_t M, int N, int K, int n_chunks, int accumulate, int dbg,
+                        int64_t batch_a, int64_t batch_bp, int64_t batch_c) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);     // swizzle atoms need 1024-byte alignment
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  A += blockIdx.z * batch_a;            // batched GEMMs (the two GRU encoders): per-batch operand offsets
+  Bp += blockIdx.z * batch_bp;
+  C += blockIdx.z * batch_c;
+  if (bias != nullptr) bias += blockIdx.z * (int64_t)N;
   const int64_t row_base = (int64_t)blockIdx.x * (2 * UM);
   const int nt = blockIdx.y;
   const int n0 = nt * UN;
@@ -530,43 +537,55 @@ static uint8_t* g_scratch = nullptr;
 static int64_t g_scratch_bytes = 0;
 void set_scratch(void* p, int64_t bytes) { g_scratch = (uint8_t*)p; g_scratch_bytes = p ? bytes : 0; }
 
+// ---- building blocks shared with gru.cu ------------------------------------------------------------------------
+int64_t umma_packed_bytes(int N, int K) {
+  return (int64_t)((N + UN - 1) / UN) * ((K + P_BK - 1) / P_BK) * P_B_CHUNK;
+}
+bool umma_shape_ok(int N, int K) { return (K % 4 == 0) && (N % 8 == 0) && N > 0 && K > 0; }
+
+// Pack logical B[k][n] = B[k*sk + n*sn] (K x N) into tiles [tile_offset, tile_offset + ceil(N/200)) of Bp.
+int umma_pack_b(const float* B, int64_t sk, int64_t sn, int N, int K, void* Bp, int tile_offset, cudaStream_t stream) {
+  const int n_tiles = (N + UN - 1) / UN, n_chunks = (K + P_BK - 1) / P_BK;
+  umma_pack_b_kernel<<<dim3(n_tiles, n_chunks, 7), 256, 0, stream>>>(B, sk, sn, N, K, (uint8_t*)Bp, n_chunks, tile_offset);
+  RENET_CHECK_LAUNCH("umma_pack_b_kernel");
+  return RENET_OK;
+}
+
+// C[b] (+)= A[b] @ Bpacked[b] (+bias[b]) for b < batch; strides in elements (A, C) / bytes (Bp).
+int umma_gemm_prepacked(const float* A, const int32_t* a_index, int64_t lda, const void* Bp, float* C, int64_t ldc,
+                        const float* bias, int64_t M, int N, int K, bool accumulate, int batch, int64_t batch_a,
+                        int64_t batch_bp, int64_t batch_c, cudaStream_t stream) {
+  if (M <= 0) return RENET_OK;
+  static bool attr2 = false;
+  if (!attr2) {
+    RENET_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+    RENET_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+    attr2 = true;
+  }
+  const int n_tiles = (N + UN - 1) / UN, n_chunks = (K + P_BK - 1) / P_BK;
+  dim3 grid((unsigned)((M + 2 * UM - 1) / (2 * UM)), (unsigned)n_tiles, (unsigned)batch);
+  if (a_index)
+    umma_gemm_packed_kernel<true><<<grid, UTHREADS, P_SMEM, stream>>>(A, a_index, lda, (const uint8_t*)Bp, C, ldc, bias, M, N, K,
+                                                                    n_chunks, accumulate, g_dbg, batch_a, batch_bp, batch_c);
+  else
+    umma_gemm_packed_kernel<false><<<grid, UTHREADS, P_SMEM, stream>>>(A, a_index, lda, (const uint8_t*)Bp, C, ldc, bias, M, N, K,
+                                                                     n_chunks, accumulate, g_dbg, batch_a, batch_bp, batch_c);
+  RENET_CHECK_LAUNCH("umma_gemm_packed_kernel");
+  return RENET_OK;
+}
+
 int umma_gemm_nn_try(const float* A, const int32_t* a_index, int64_t lda, const float* B, int64_t ldb, float* C,
                      int64_t ldc, const float* bias, int64_t M, int32_t N, int32_t K, bool accumulate,
                      cudaStream_t stream) {
   const bool aligned = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C) |
                          reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
-  // ---- packed path (v2): needs the registered scratch buffer for the packed copy of B ------------------------
-  {
-    const int n_tiles = (N + UN - 1) / UN, n_chunks = (K + P_BK - 1) / P_BK;
-    const int64_t need = (int64_t)n_tiles * n_chunks * P_B_CHUNK;
-    const bool ok2 = aligned && (K % 4 == 0) && (N % 8 == 0) && (lda % 4 == 0) && (ldc % 4 == 0) && M >= 64 &&
-                     g_scratch != nullptr && need <= g_scratch_bytes &&
-                     (reinterpret_cast<uintptr_t>(g_scratch) & 127) == 0;
-    if (ok2) {
-      static bool attr2 = false;
-      if (!attr2) {
-        cudaError_t e1 = cudaFuncSetAttribute(umma_gemm_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
-        cudaError_t e2 = cudaFuncSetAttribute(umma_gemm_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) {
-          set_error("cudaFuncSetAttribute(umma_gemm_packed_kernel) failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-          return RENET_ERR_CUDA;
-        }
-        attr2 = true;
-      }
-      if (!(g_dbg & 32)) umma_pack_b_kernel<<<dim3(n_tiles, n_chunks, 7), 256, 0, stream>>>(B, ldb, N, K, g_scratch, n_chunks);
-      dim3 grid((unsigned)((M + 2 * UM - 1) / (2 * UM)), (unsigned)n_tiles);
-      if (a_index)
-        umma_gemm_packed_kernel<true><<<grid, UTHREADS, P_SMEM, stream>>>(A, a_index, lda, g_scratch, C, ldc, bias, M, N, K, n_chunks, accumulate, g_dbg);
-      else
-        umma_gemm_packed_kernel<false><<<grid, UTHREADS, P_SMEM, stream>>>(A, a_index, lda, g_scratch, C, ldc, bias, M, N, K, n_chunks, accumulate, g_dbg);
-      cudaError_t e = cudaGetLastError();
-      if (e != cudaSuccess) {
-        set_error("launch of umma_gemm_packed_kernel failed: %s", cudaGetErrorString(e));
-        return RENET_ERR_CUDA;
-      }
-      count_launch(2);
-      return 1;
-    }
+  // ---- packed path: needs the registered scratch buffer for the packed copy of B ---------------------------------
+  if (aligned && umma_shape_ok(N, K) && (lda % 4 == 0) && (ldc % 4 == 0) && M >= 64 && g_scratch != nullptr &&
+      umma_packed_bytes(N, K) <= g_scratch_bytes && (reinterpret_cast<uintptr_t>(g_scratch) & 127) == 0) {
+    int rc = (g_dbg & 32) ? 0 : umma_pack_b(B, ldb, 1, N, K, g_scratch, 0, stream);
+    if (rc) return rc;
+    rc = umma_gemm_prepacked(A, a_index, lda, g_scratch, C, ldc, bias, M, N, K, accumulate, 1, 0, 0, 0, stream);
+    return rc ? rc : 1;
   }
   const bool ok = (K % UKC == 0) && K >= UKC && (N % 8 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) &&
                   M >= 64 && aligned;
