@@ -69,6 +69,12 @@ class RGCNAggregator(nn.Module):
     # ---------------------------------------------------------------------------------------------
     def _batch(self, s_hist, s, graph_dict, device, sort):
         from .hoststore import HistoryView, assemble_view
+        from .utils import HistoryBatch
+        if isinstance(s_hist, HistoryBatch):         # already assembled and uploaded (hoststore.prefetch)
+            if s_hist.graph is None:
+                raise ValueError('RGCNAggregator: every history in the batch is empty '
+                                 '(the reference fails on this input too, Aggregator.py:128-129,167)')
+            return s_hist
         if isinstance(s_hist, HistoryView):          # flat stores + C++ batcher (renet_host_assemble_batch)
             if s_hist.total_length() == 0:
                 raise ValueError('RGCNAggregator: every history in the batch is empty '

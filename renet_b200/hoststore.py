@@ -180,26 +180,26 @@ def split_raw(buf, r):
     return out
 
 
-def assemble_view(view, device, sort=True):
-    """HistoryView -> HistoryBatch on ``device`` through the C++ batcher (one pinned H2D copy)."""
-    st = _staging.get(str(device))
-    if st is None:
-        st = _staging[str(device)] = _Staging()
-    slot, buf = st.next()
-    r = assemble_view_raw(view, buf.numpy(), sort)
+def _stage(view, buf_holder, sort):
+    """Host part: run the C++ batcher into a pinned buffer (grows it when needed).  Thread-safe per buffer."""
+    r = assemble_view_raw(view, buf_holder[0].numpy(), sort)
     if 'need_words' in r:
-        st.bufs[slot] = buf = torch.empty(int(r['need_words'] * 1.5), dtype=torch.int32).pin_memory()
-        r = assemble_view_raw(view, buf.numpy(), sort)
+        buf_holder[0] = torch.empty(int(r['need_words'] * 1.5), dtype=torch.int32).pin_memory()
+        r = assemble_view_raw(view, buf_holder[0].numpy(), sort)
+    return r
+
+
+def _upload(view, buf, r, device):
+    """Device part (caller's thread / current stream): one pinned H2D copy, then slice it into the batch."""
     hb = HistoryBatch()
     hb.s_idx, hb.num_seq, hb.S = r['s_idx'], r['Q'], r['S']
     if r['S'] == 0:
         hb.graph, hb.seq_len = None, np.zeros(0, np.int64)
-        return hb
+        return hb, None
     words = r['words']
     dev = buf[:words].to(device, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
-    st.events[slot] = ev
     d = split_raw(dev, r)
     h = split_raw(buf.numpy(), r)
     g = BatchedHistoryGraph.__new__(BatchedHistoryGraph)
@@ -224,4 +224,59 @@ def assemble_view(view, device, sort=True):
     hb.batch_sizes = r['batch_sizes']
     hb.times = view.store.gs.times[r['comp_graph']]
     hb.h2d_bytes = words * 4
+    return hb, ev
+
+
+def assemble_view(view, device, sort=True):
+    """HistoryView -> HistoryBatch on ``device`` through the C++ batcher (one pinned H2D copy)."""
+    st = _staging.get(str(device))
+    if st is None:
+        st = _staging[str(device)] = _Staging()
+    slot, buf = st.next()
+    holder = [buf]
+    r = _stage(view, holder, sort)
+    st.bufs[slot] = holder[0]
+    hb, ev = _upload(view, holder[0], r, device)
+    st.events[slot] = ev
     return hb
+
+
+def prefetch(view_groups, device, depth=2, workers=4, sort=True):
+    """Pipeline the host batching: ``view_groups`` is an iterable of tuples of HistoryViews (one tuple per step,
+    e.g. (subject view, object view)); yields tuples of HistoryBatches on ``device``.  While the consumer runs
+    step i on the GPU, worker threads run the C++ batcher (which releases the GIL) for steps i+1 .. i+depth into
+    their own pinned staging buffers; the H2D copy is issued from the consumer's thread on its current stream."""
+    import collections
+    from concurrent.futures import ThreadPoolExecutor
+    free = collections.deque()
+    pending = collections.deque()
+    it = iter(view_groups)
+
+    def job(view):
+        holder = [free.pop() if free else torch.empty(1 << 21, dtype=torch.int32).pin_memory()]
+        return view, holder, _stage(view, holder, sort)
+
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        def submit():
+            try:
+                grp = next(it)
+            except StopIteration:
+                return False
+            pending.append([pool.submit(job, v) for v in grp])
+            return True
+        for _ in range(depth):
+            if not submit():
+                break
+        in_flight = collections.deque()       # (event, buffer) of uploads whose pinned buffer is not reusable yet
+        while pending:
+            futs = pending.popleft()
+            out = []
+            for f in futs:
+                view, holder, r = f.result()
+                hb, ev = _upload(view, holder[0], r, device)
+                out.append(hb)
+                in_flight.append((ev, holder[0]))
+            submit()
+            while in_flight and (in_flight[0][0] is None or in_flight[0][0].query()):
+                free.append(in_flight.popleft()[1])
+            yield tuple(out)

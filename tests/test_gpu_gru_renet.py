@@ -159,3 +159,22 @@ def test_cpp_batcher_path_equals_list_path():
             c = m.encode(batch, vs, vo, gs, subject=subj)
             for x, y in zip(a[:5], c[:5]):
                 assert torch.allclose(x.float(), y.float(), atol=1e-5)
+
+
+def test_prefetched_batches_equal_direct_assembly():
+    """hoststore.prefetch (worker threads + pinned staging ring) yields the same device batches as assemble_view."""
+    from renet_b200 import hoststore, synthetic
+    tkg = synthetic.SyntheticTKG('icews18', seed=4, num_timestamps=16)
+    gs = hoststore.GraphStore(tkg.graph_dict)
+    hs = hoststore.HistoryStore(tkg.s_hist, tkg.s_hist_t, tkg.quads[:, 0], gs)
+    sels = [tkg.batch_indices(i, 256) for i in range(5)]
+    dev = torch.device(DEV)
+    got = list(hoststore.prefetch(((hs.select(s),) for s in sels), dev, depth=2, workers=2))
+    assert len(got) == 5
+    for (hb,), s in zip(got, sels):
+        ref = hoststore.assemble_view(hs.select(s), dev)
+        for name in ('node_ent', 'row_ptr', 'col_src', 'col_type_s', 'col_type_o', 'norm'):
+            assert torch.equal(getattr(hb.graph, name), getattr(ref.graph, name)), name
+        assert torch.equal(hb.readout, ref.readout) and torch.equal(hb.packed_row, ref.packed_row)
+        np.testing.assert_array_equal(hb.s_idx, ref.s_idx)
+        np.testing.assert_array_equal(hb.batch_sizes, ref.batch_sizes)
