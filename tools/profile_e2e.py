@@ -22,29 +22,40 @@ m.global_emb = {t: v.to(dev) for t, v in tkg.global_emb.items()}
 sels = [tkg.batch_indices(i, 1024, tail_only=False) for i in range(6)]
 
 
-def step(i):
-    sel = sels[i % len(sels)]
-    batch = torch.from_numpy(tkg.quads[sel]).pin_memory().to(dev, non_blocking=True)
-    outs = []
-    with torch.no_grad():
-        for subj in (True, False):
-            s, r, o, s_h, s_q, _ = m.encode(batch, hs_s.select(sel), hs_o.select(sel), gs, subject=subj)
-            outs.append(torch.cat((s_h, s_q), 1))
-    return torch.cat(outs).cpu()
+def run(n, first):
+    idx = [(first + i) % len(sels) for i in range(n)]
+    groups = ((hs_s.select(sels[j]), hs_o.select(sels[j])) for j in idx)
+    for j, hbs in zip(idx, hoststore.prefetch(groups, dev, depth=2, workers=4)):
+        batch = torch.from_numpy(tkg.quads[sels[j]]).pin_memory().to(dev, non_blocking=True)
+        outs = []
+        with torch.no_grad():
+            for subj in (True, False):
+                s, r, o, s_h, s_q, _ = m.encode(batch, hbs[0], hbs[1], gs, subject=subj)
+                outs.append(torch.cat((s_h, s_q), 1))
+        torch.cat(outs).cpu()
 
 
-for i in range(3):
-    step(i)
+run(4, 0)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-for i in range(10):
-    step(i)
+run(20, 0)
 torch.cuda.synchronize()
-print('e2e step %.2f ms' % ((time.perf_counter() - t0) / 10 * 1e3))
+print('e2e step (prefetch) %.2f ms' % ((time.perf_counter() - t0) / 20 * 1e3))
+# GPU-only time of the same work
+hbs_all = [(hoststore.assemble_view(hs_s.select(sels[j]), dev), hoststore.assemble_view(hs_o.select(sels[j]), dev)) for j in range(3)]
+batch = torch.from_numpy(tkg.quads[sels[0]]).to(dev)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0 = time.perf_counter(); a.record()
+with torch.no_grad():
+    for k in range(10):
+        for subj in (True, False):
+            m.encode(batch, hbs_all[k % 3][0], hbs_all[k % 3][1], gs, subject=subj)
+b.record(); torch.cuda.synchronize()
+print('encode x2 without batching/copies: GPU %.2f ms, wall %.2f ms per step' % (a.elapsed_time(b) / 10, (time.perf_counter() - t0) / 10 * 1e3))
 pr = cProfile.Profile()
 pr.enable()
-for i in range(10):
-    step(i)
+run(10, 0)
 pr.disable()
 st = pstats.Stats(pr)
-st.sort_stats('cumulative').print_stats(28)
+st.sort_stats('tottime').print_stats(22)
