@@ -104,6 +104,7 @@ __global__ void pack_inputs_kernel(const float* __restrict__ H2, const int32_t* 
 struct GruWs {
   float *Brow, *Bent, *Brel, *Bglob, *Whh, *bih, *bhh, *GI, *PQ, *PT, *GH, *Hs;
   float *P_row, *P_ent, *P_rel, *P_glob, *P_hh;   // tensor-core engine: weights packed for umma_gemm_prepacked
+  float* sync;                                      // grid-barrier counter of the persistent recurrence kernel
   int64_t p_hh_bytes;
   int64_t total_floats;
 };
@@ -133,6 +134,7 @@ GruWs carve(float* base, int64_t S, int64_t Q, int64_t T, int h, int max_len) {
   w.P_glob = take(umma_packed_bytes(6 * h, h) / 4);
   w.p_hh_bytes = umma_packed_bytes(3 * h, h);
   w.P_hh = take(2 * w.p_hh_bytes / 4);
+  w.sync = take(32);
   w.total_floats = off;
   return w;
 }
@@ -144,6 +146,11 @@ constexpr int kMaxLenWs = 16;  // workspace is sized for sequences up to this lo
 int64_t gru_workspace_floats(int64_t S, int64_t Q, int64_t T, int h) {
   return carve(nullptr, S, Q, T, h, kMaxLenWs).total_floats;
 }
+
+int launch_gru_recur(const float* GI, const float* PQ, const float* PT, const float* bhh, const int32_t* row_glob,
+                     const int32_t* seq_start, const int32_t* seq_len, const float* w_hh4, const float* w_hh3, float* Hs,
+                     float* GH, float* hn4, float* hn3, unsigned int* barrier_counter, const int32_t* host_batch_sizes,
+                     int max_len, int64_t Q, int h, cudaStream_t stream);
 
 int launch_pack_inputs(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
                        const float* ent, const float* rel, const int32_t* row_seq, const int32_t* seq_s,
@@ -200,6 +207,12 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
     if ((rc = umma_gemm_prepacked(ent, seq_s, h, w.P_ent, w.PQ, 6 * h, w.bih, Q, 6 * h, h, false, 1, 0, 0, 0, stream))) return rc;
     if ((rc = umma_gemm_prepacked(rel, seq_r, h, w.P_rel, w.PQ, 6 * h, nullptr, Q, 3 * h, h, true, 1, 0, 0, 0, stream))) return rc;
     if ((rc = umma_gemm_prepacked(glob, nullptr, h, w.P_glob, w.PT, 6 * h, nullptr, T, 6 * h, h, false, 1, 0, 0, 0, stream))) return rc;
+    // recurrence: one persistent cooperative tensor-core kernel for all time steps and both encoders (gru_recur.cu);
+    // the step-by-step loop below is the fallback for shapes it does not take
+    rc = launch_gru_recur(w.GI, w.PQ, w.PT, w.bhh, row_glob, seq_start, seq_len, w_hh4, w_hh3, w.Hs, w.GH, hn4, hn3,
+                          reinterpret_cast<unsigned int*>(w.sync), host_batch_sizes, max_len, Q, h, stream);
+    if (rc < 0) return rc;
+    if (rc == 1) return RENET_OK;
     const int64_t hs_stride_u = Q * 2 * h;
     for (int t = 0; t < max_len; ++t) {
       const int n_act = host_batch_sizes[t];

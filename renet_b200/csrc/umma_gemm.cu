@@ -20,6 +20,7 @@
 //   * accumulator: 128 lanes x 208 fp32 columns of TMEM (256 allocated); epilogue reads it with
 //     tcgen05.ld 32x32b (thread = row) and writes C with bias / accumulate applied.
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace renet {
 namespace {
@@ -39,72 +40,7 @@ constexpr int NUM_STAGES = 2;
 constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 64;   // + mbarriers / tmem pointer
 constexpr int TMEM_COLS = 256;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-// Bounded spin: a wrong descriptor must fail the launch (trap), never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (int spins = 0; !done; ++spins) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (spins > (1 << 20)) __trap();
-  }
-}
-
-// K-major, no swizzle: LBO = byte distance between the two 16-byte K-slabs of one MMA, SBO = byte
-// distance between consecutive 8-row core matrices; version = 1 (Blackwell).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-
-// kind::tf32, fp32 accumulate, A and B K-major, M=128, N=208
-__device__ __forceinline__ uint32_t make_idesc() {
-  uint32_t d = 0;
-  d |= 1u << 4;                 // c_format = F32
-  d |= 2u << 7;                 // a_format = TF32
-  d |= 2u << 10;                // b_format = TF32
-  d |= (uint32_t)(UNP >> 3) << 17;
-  d |= (uint32_t)(UM >> 4) << 24;
-  return d;
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-  lo = v - hi;
-}
-__device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
-  split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
-  split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-}
+__device__ __forceinline__ uint32_t make_idesc() { return make_idesc_n(UNP); }
 
 template <bool INDEXED>
 __global__ void __launch_bounds__(UTHREADS, 1)
@@ -288,20 +224,6 @@ constexpr int P_A_BYTES = UM * 128;                  // 16384
 constexpr int P_B_BYTES = UNP * 128;                 // 26624
 constexpr int P_B_CHUNK = 2 * P_B_BYTES;             // hi + lo planes of one (tile, chunk)
 constexpr int P_SMEM = 4 * P_A_BYTES + 2 * P_B_CHUNK + 1024 + 128;   // two tiles' A (hi,lo) + two B stages
-
-__device__ __forceinline__ uint32_t sw128_offset(int row, int chunk16) {
-  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk16 ^ (row & 7)) << 4));
-}
-// K-major SWIZZLE_128B descriptor: SBO = 1024 B (8 rows x 128 B), LBO field = 1, version 1, layout type 2
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 
 // Bp[(nt * n_chunks + kc)] = {hi plane, lo plane} of B[kc*32 .. +31][nt*200 .. +207] (zero padded)
 __global__ void __launch_bounds__(256)
