@@ -118,50 +118,106 @@ gru_recur_kernel(const float* __restrict__ GI, const float* __restrict__ PQ, con
     float* GHt = GH + (int64_t)t * Q * 6 * h;
     for (int mt = blockIdx.z; mt < n_mtiles && mt * 128 < n_act; mt += gridDim.z) {
       const int q0 = mt * 128;
+      const int q = q0 + erow;
+      const bool qv = q < n_act;
+      // ---- (1) everything that does not depend on the MMAs is fetched first: all K chunks of this tile's h_{t-1} rows
+      //          (registers) and the input-projection sums GI[row] + PQ[q] + PT[timestamp] + b_hh of the thread's 16 units
+      float4 areg[R_MAX_CHUNKS][4];
       if (t > 0) {
-        // ---- gh = h_{t-1}[tile] @ W_hh_slice^T on the tensor cores ------------------------------------------------------
-        for (int c = 0; c < n_chunks; ++c) {
-          if (a_uses > 0) { mbar_wait(bar0, afree_phase); afree_phase ^= 1; }       // previous MMAs have read sA
-          ++a_uses;
-          const int k0 = c * R_BK;
+#pragma unroll
+        for (int c = 0; c < R_MAX_CHUNKS; ++c) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int task = tid + i * R_THREADS;
             const int r = task >> 3, j = task & 7;
-            const int q = q0 + r, k = k0 + 4 * j;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (q < n_act && k < h) v = ldcg_f4(Hprev + (int64_t)q * 2 * h + enc * h + k);
-            float4 hi, lo;
-            split4(v, hi, lo);
-            const uint32_t off = sw128_offset(r, j);
-            *reinterpret_cast<float4*>(sA + off) = hi;
-            *reinterpret_cast<float4*>(sA + R_A_BYTES + off) = lo;
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncthreads();
-          if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = smem_base + R_MAX_CHUNKS * 2 * R_B_PLANE, a_lo = a_hi + R_A_BYTES;
-            const uint32_t b_hi = smem_base + c * 2 * R_B_PLANE, b_lo = b_hi + R_B_PLANE;
-#pragma unroll
-            for (int ks = 0; ks < R_BK / 8; ++ks) {
-              const uint32_t ko = ks * 32;
-              const uint64_t dAh = make_desc_sw128(a_hi + ko), dAl = make_desc_sw128(a_lo + ko);
-              const uint64_t dBh = make_desc_sw128(b_hi + ko), dBl = make_desc_sw128(b_lo + ko);
-              umma_tf32(tmem_base, dAh, dBh, idesc, (c | ks) != 0);
-              umma_tf32(tmem_base, dAl, dBh, idesc, 1);
-              umma_tf32(tmem_base, dAh, dBl, idesc, 1);
-            }
-            umma_commit(bar0);
-            if (c == n_chunks - 1) umma_commit(bar0 + 8);
+            const int qq = q0 + r, k = c * R_BK + 4 * j;
+            areg[c][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < n_chunks && qq < n_act && k < h) areg[c][i] = ldcg_f4(Hprev + (int64_t)qq * 2 * h + enc * h + k);
           }
         }
+      }
+      float pre[3][16], bhn[16];            // b_hh of the r and z gates is folded into pre; the n gate needs it apart
+      int64_t row = 0;
+      bool last = false;
+      if (qv) {
+        row = (int64_t)__ldg(seq_start + q) + t;
+        const int64_t gl = (int64_t)__ldg(row_glob + row);
+        last = (t == __ldg(seq_len + q) - 1);
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          const int u = u0 + eu0 + 4 * v4;
+          const bool uv = u < h;
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            const int col = enc * 3 * h + g * h + u;
+            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4, c4 = a4, bb = a4;
+            if (uv) {
+              a4 = ldg_f4(GI + row * 6 * h + col); b4 = ldg_f4(PQ + (int64_t)q * 6 * h + col);
+              c4 = ldg_f4(PT + gl * 6 * h + col); bb = ldg_f4(bhh + col);
+            }
+            pre[g][4 * v4 + 0] = a4.x + b4.x + c4.x; pre[g][4 * v4 + 1] = a4.y + b4.y + c4.y;
+            pre[g][4 * v4 + 2] = a4.z + b4.z + c4.z; pre[g][4 * v4 + 3] = a4.w + b4.w + c4.w;
+            if (g < 2) {
+              pre[g][4 * v4 + 0] += bb.x; pre[g][4 * v4 + 1] += bb.y; pre[g][4 * v4 + 2] += bb.z; pre[g][4 * v4 + 3] += bb.w;
+            } else {
+              bhn[4 * v4 + 0] = bb.x; bhn[4 * v4 + 1] = bb.y; bhn[4 * v4 + 2] = bb.z; bhn[4 * v4 + 3] = bb.w;
+            }
+          }
+        }
+      }
+      if (t > 0) {
+        // ---- (2) gh = h_{t-1}[tile] @ W_hh_slice^T on the tensor cores: per chunk only split + store + 12 MMAs ----------
+#pragma unroll
+        for (int c = 0; c < R_MAX_CHUNKS; ++c) {
+          if (c < n_chunks) {
+            if (a_uses > 0) { mbar_wait(bar0, afree_phase); afree_phase ^= 1; }       // previous MMAs have read sA
+            ++a_uses;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int task = tid + i * R_THREADS;
+              const int r = task >> 3, j = task & 7;
+              float4 hi, lo;
+              split4(areg[c][i], hi, lo);
+              const uint32_t off = sw128_offset(r, j);
+              *reinterpret_cast<float4*>(sA + off) = hi;
+              *reinterpret_cast<float4*>(sA + R_A_BYTES + off) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t a_hi = smem_base + R_MAX_CHUNKS * 2 * R_B_PLANE, a_lo = a_hi + R_A_BYTES;
+              const uint32_t b_hi = smem_base + c * 2 * R_B_PLANE, b_lo = b_hi + R_B_PLANE;
+#pragma unroll
+              for (int ks = 0; ks < R_BK / 8; ++ks) {
+                const uint32_t ko = ks * 32;
+                const uint64_t dAh = make_desc_sw128(a_hi + ko), dAl = make_desc_sw128(a_lo + ko);
+                const uint64_t dBh = make_desc_sw128(b_hi + ko), dBl = make_desc_sw128(b_lo + ko);
+                umma_tf32(tmem_base, dAh, dBh, idesc, (c | ks) != 0);
+                umma_tf32(tmem_base, dAl, dBh, idesc, 1);
+                umma_tf32(tmem_base, dAh, dBl, idesc, 1);
+              }
+              umma_commit(bar0);
+              if (c == n_chunks - 1) umma_commit(bar0 + 8);
+            }
+          }
+        }
+      }
+      float hpv[16];                          // the thread's own h_{t-1} values: fetched while the last MMAs drain
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4) {
+        const int u = u0 + eu0 + 4 * v4;
+        float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t > 0 && qv && u < h) hp = ldcg_f4(Hprev + (int64_t)q * 2 * h + enc * h + u);
+        hpv[4 * v4 + 0] = hp.x; hpv[4 * v4 + 1] = hp.y; hpv[4 * v4 + 2] = hp.z; hpv[4 * v4 + 3] = hp.w;
+      }
+      if (t > 0) {
         mbar_wait(bar0 + 8, mma_phase);
         mma_phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
-      // ---- epilogue: gates for (sequence erow, units eu0 .. eu0+15 of the slice) -----------------------------------------
+      // ---- (3) epilogue: gates for (sequence erow, units eu0 .. eu0+15 of the slice) -------------------------------------
       uint32_t acc[3][16];
       if (t > 0) {
 #pragma unroll
@@ -176,42 +232,32 @@ gru_recur_kernel(const float* __restrict__ GI, const float* __restrict__ PQ, con
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       }
-      const int q = q0 + erow;
-      if (q < n_act) {
-        const int64_t row = (int64_t)__ldg(seq_start + q) + t;
-        const int64_t gl = (int64_t)__ldg(row_glob + row);
-        const bool last = (t == __ldg(seq_len + q) - 1);
+      if (qv) {
         float* hn = enc == 0 ? hn4 : hn3;
 #pragma unroll
         for (int v4 = 0; v4 < 4; ++v4) {                 // 4 units at a time (16-byte accesses)
           const int u = u0 + eu0 + 4 * v4;
-          if (u >= h) break;
-          float pre[3][4], ghv[3][4];
+          if (u < h) {
+            float gh[3][4];
 #pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            const int col = enc * 3 * h + g * h + u;
-            const float4 a = ldg_f4(GI + row * 6 * h + col), b = ldg_f4(PQ + (int64_t)q * 6 * h + col),
-                         c4 = ldg_f4(PT + gl * 6 * h + col), bb = ldg_f4(bhh + col);
-            pre[g][0] = a.x + b.x + c4.x; pre[g][1] = a.y + b.y + c4.y;
-            pre[g][2] = a.z + b.z + c4.z; pre[g][3] = a.w + b.w + c4.w;
-            const float m0 = t > 0 ? __uint_as_float(acc[g][4 * v4 + 0]) : 0.f, m1 = t > 0 ? __uint_as_float(acc[g][4 * v4 + 1]) : 0.f,
-                        m2 = t > 0 ? __uint_as_float(acc[g][4 * v4 + 2]) : 0.f, m3 = t > 0 ? __uint_as_float(acc[g][4 * v4 + 3]) : 0.f;
-            if (t > 0) st_f4(GHt + (int64_t)q * 6 * h + col, make_float4(m0, m1, m2, m3));   // saved for backward
-            ghv[g][0] = m0 + bb.x; ghv[g][1] = m1 + bb.y; ghv[g][2] = m2 + bb.z; ghv[g][3] = m3 + bb.w;
-          }
-          float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (t > 0) hp = ldcg_f4(Hprev + (int64_t)q * 2 * h + enc * h + u);
-          const float hpv[4] = {hp.x, hp.y, hp.z, hp.w};
-          float o[4];
+            for (int g = 0; g < 3; ++g) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float r = sigm(pre[0][i] + ghv[0][i]);
-            const float z = sigm(pre[1][i] + ghv[1][i]);
-            const float n = tanhf(pre[2][i] + r * ghv[2][i]);
-            o[i] = (1.f - z) * n + z * hpv[i];
+              for (int i = 0; i < 4; ++i) gh[g][i] = t > 0 ? __uint_as_float(acc[g][4 * v4 + i]) : 0.f;
+              if (t > 0)   // recurrent pre-activations (without bias), saved for backward
+                st_f4(GHt + (int64_t)q * 6 * h + enc * 3 * h + g * h + u, make_float4(gh[g][0], gh[g][1], gh[g][2], gh[g][3]));
+            }
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int x = 4 * v4 + i;
+              const float r = sigm(pre[0][x] + gh[0][i]);
+              const float z = sigm(pre[1][x] + gh[1][i]);
+              const float n = tanhf(pre[2][x] + r * (gh[2][i] + bhn[x]));
+              o[i] = (1.f - z) * n + z * hpv[x];
+            }
+            st_f4(Hnext + (int64_t)q * 2 * h + enc * h + u, make_float4(o[0], o[1], o[2], o[3]));
+            if (last) st_f4(hn + (int64_t)q * h + u, make_float4(o[0], o[1], o[2], o[3]));
           }
-          st_f4(Hnext + (int64_t)q * 2 * h + enc * h + u, make_float4(o[0], o[1], o[2], o[3]));
-          if (last) st_f4(hn + (int64_t)q * h + u, make_float4(o[0], o[1], o[2], o[3]));
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
