@@ -11,6 +11,8 @@
 //     recurrent pre-activations GH, which the backward pass re-uses);
 //   * steps are separated by a grid-wide barrier (atomic counter; the launch is cooperative so all CTAs are resident).
 // Outputs match gru.cu's step-by-step path bit-for-bit in layout: Hs [(L+1), Q, 2h], GH [L, Q, 6h], hn4, hn3.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -54,7 +56,7 @@ gru_recur_kernel(const float* __restrict__ GI, const float* __restrict__ PQ, con
                  const int32_t* __restrict__ seq_start, const int32_t* __restrict__ seq_len,
                  const float* __restrict__ w_hh4, const float* __restrict__ w_hh3, float* __restrict__ Hs,
                  float* __restrict__ GH, float* __restrict__ hn4, float* __restrict__ hn3, unsigned int* barrier_counter,
-                 StepCounts counts, int max_len, int Q, int h) {
+                 StepCounts counts, int max_len, int Q, int h, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);
@@ -119,11 +121,11 @@ gru_recur_kernel(const float* __restrict__ GI, const float* __restrict__ PQ, con
     for (int mt = blockIdx.z; mt < n_mtiles && mt * 128 < n_act; mt += gridDim.z) {
       const int q0 = mt * 128;
       const int q = q0 + erow;
-      const bool qv = q < n_act;
+      const bool qv = q < n_act && !(dbg & 1);
       // ---- (1) everything that does not depend on the MMAs is fetched first: all K chunks of this tile's h_{t-1} rows
       //          (registers) and the input-projection sums GI[row] + PQ[q] + PT[timestamp] + b_hh of the thread's 16 units
       float4 areg[R_MAX_CHUNKS][4];
-      if (t > 0) {
+      if (t > 0 && !(dbg & 8)) {
 #pragma unroll
         for (int c = 0; c < R_MAX_CHUNKS; ++c) {
 #pragma unroll
@@ -136,36 +138,7 @@ gru_recur_kernel(const float* __restrict__ GI, const float* __restrict__ PQ, con
           }
         }
       }
-      float pre[3][16], bhn[16];            // b_hh of the r and z gates is folded into pre; the n gate needs it apart
-      int64_t row = 0;
-      bool last = false;
-      if (qv) {
-        row = (int64_t)__ldg(seq_start + q) + t;
-        const int64_t gl = (int64_t)__ldg(row_glob + row);
-        last = (t == __ldg(seq_len + q) - 1);
-#pragma unroll
-        for (int v4 = 0; v4 < 4; ++v4) {
-          const int u = u0 + eu0 + 4 * v4;
-          const bool uv = u < h;
-#pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            const int col = enc * 3 * h + g * h + u;
-            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4, c4 = a4, bb = a4;
-            if (uv) {
-              a4 = ldg_f4(GI + row * 6 * h + col); b4 = ldg_f4(PQ + (int64_t)q * 6 * h + col);
-              c4 = ldg_f4(PT + gl * 6 * h + col); bb = ldg_f4(bhh + col);
-            }
-            pre[g][4 * v4 + 0] = a4.x + b4.x + c4.x; pre[g][4 * v4 + 1] = a4.y + b4.y + c4.y;
-            pre[g][4 * v4 + 2] = a4.z + b4.z + c4.z; pre[g][4 * v4 + 3] = a4.w + b4.w + c4.w;
-            if (g < 2) {
-              pre[g][4 * v4 + 0] += bb.x; pre[g][4 * v4 + 1] += bb.y; pre[g][4 * v4 + 2] += bb.z; pre[g][4 * v4 + 3] += bb.w;
-            } else {
-              bhn[4 * v4 + 0] = bb.x; bhn[4 * v4 + 1] = bb.y; bhn[4 * v4 + 2] = bb.z; bhn[4 * v4 + 3] = bb.w;
-            }
-          }
-        }
-      }
-      if (t > 0) {
+      if (t > 0 && !(dbg & 2)) {
         // ---- (2) gh = h_{t-1}[tile] @ W_hh_slice^T on the tensor cores: per chunk only split + store + 12 MMAs ----------
 #pragma unroll
         for (int c = 0; c < R_MAX_CHUNKS; ++c) {
@@ -204,67 +177,81 @@ gru_recur_kernel(const float* __restrict__ GI, const float* __restrict__ PQ, con
           }
         }
       }
-      float hpv[16];                          // the thread's own h_{t-1} values: fetched while the last MMAs drain
-#pragma unroll
-      for (int v4 = 0; v4 < 4; ++v4) {
-        const int u = u0 + eu0 + 4 * v4;
-        float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t > 0 && qv && u < h) hp = ldcg_f4(Hprev + (int64_t)q * 2 * h + enc * h + u);
-        hpv[4 * v4 + 0] = hp.x; hpv[4 * v4 + 1] = hp.y; hpv[4 * v4 + 2] = hp.z; hpv[4 * v4 + 3] = hp.w;
-      }
-      if (t > 0) {
+      if (t > 0 && !(dbg & 2)) {
         mbar_wait(bar0 + 8, mma_phase);
         mma_phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
-      // ---- (3) epilogue: gates for (sequence erow, units eu0 .. eu0+15 of the slice) -------------------------------------
-      uint32_t acc[3][16];
-      if (t > 0) {
-#pragma unroll
-        for (int g = 0; g < 3; ++g) {
-          const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * RU + eu0);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-              : "=r"(acc[g][0]), "=r"(acc[g][1]), "=r"(acc[g][2]), "=r"(acc[g][3]), "=r"(acc[g][4]), "=r"(acc[g][5]),
-                "=r"(acc[g][6]), "=r"(acc[g][7]), "=r"(acc[g][8]), "=r"(acc[g][9]), "=r"(acc[g][10]), "=r"(acc[g][11]),
-                "=r"(acc[g][12]), "=r"(acc[g][13]), "=r"(acc[g][14]), "=r"(acc[g][15])
-              : "r"(taddr));
-        }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      }
-      if (qv) {
-        float* hn = enc == 0 ? hn4 : hn3;
-#pragma unroll
-        for (int v4 = 0; v4 < 4; ++v4) {                 // 4 units at a time (16-byte accesses)
-          const int u = u0 + eu0 + 4 * v4;
-          if (u < h) {
-            float gh[3][4];
+      // ---- (3) epilogue.  TMEM hands every thread one ROW (sequence) of the accumulator, but all global operands are
+      //      row-major: the tile goes through shared memory (the free A buffer, two halves of 64 rows) and is then
+      //      processed one row per warp with lane = hidden unit, so every global access is a coalesced 128-byte segment
+      //      (an SM only sustains ~50 GB/s from L2: the strided version moved 2.4x the bytes and cost 19 us per step).
+      constexpr int TS = RN + 4;                           // padded row stride: conflict-free 16-byte stores
+      float* sT = reinterpret_cast<float*>(sA);            // [64 rows][100] floats = 25.6 KB
+#pragma unroll 1
+      for (int half_rows = 0; half_rows < 2; ++half_rows) {
+        if (t > 0 && !(dbg & 2)) {
+          if ((erow >> 6) == half_rows) {
 #pragma unroll
             for (int g = 0; g < 3; ++g) {
+              uint32_t v[16];
+              const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * RU + eu0);
+              asm volatile(
+                  "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                    "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                  : "r"(taddr));
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              float* dst = sT + (erow & 63) * TS + g * RU + eu0;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) gh[g][i] = t > 0 ? __uint_as_float(acc[g][4 * v4 + i]) : 0.f;
-              if (t > 0)   // recurrent pre-activations (without bias), saved for backward
-                st_f4(GHt + (int64_t)q * 6 * h + enc * 3 * h + g * h + u, make_float4(gh[g][0], gh[g][1], gh[g][2], gh[g][3]));
+              for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                                                  __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
             }
-            float o[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int x = 4 * v4 + i;
-              const float r = sigm(pre[0][x] + gh[0][i]);
-              const float z = sigm(pre[1][x] + gh[1][i]);
-              const float n = tanhf(pre[2][x] + r * (gh[2][i] + bhn[x]));
-              o[i] = (1.f - z) * n + z * hpv[x];
-            }
-            st_f4(Hnext + (int64_t)q * 2 * h + enc * h + u, make_float4(o[0], o[1], o[2], o[3]));
-            if (last) st_f4(hn + (int64_t)q * h + u, make_float4(o[0], o[1], o[2], o[3]));
           }
         }
+        __syncthreads();
+        const int u = u0 + lane;
+        float* hn = enc == 0 ? hn4 : hn3;
+        if (u < h && !(dbg & 1)) {
+          const float b_r = __ldg(bhh + enc * 3 * h + u), b_z = __ldg(bhh + enc * 3 * h + h + u),
+                      b_n = __ldg(bhh + enc * 3 * h + 2 * h + u);
+#pragma unroll 4
+          for (int rr = warp; rr < 64; rr += 8) {          // one row per warp per iteration, lane = unit
+            const int q = q0 + half_rows * 64 + rr;
+            if (q >= n_act) break;
+            const int64_t row = (int64_t)__ldg(seq_start + q) + t;
+            const int64_t gl = (int64_t)__ldg(row_glob + row);
+            const float* gi = GI + row * 6 * h + enc * 3 * h + u;
+            const float* pq = PQ + (int64_t)q * 6 * h + enc * 3 * h + u;
+            const float* pt = PT + gl * 6 * h + enc * 3 * h + u;
+            const float i_r = __ldg(gi) + __ldg(pq) + __ldg(pt);
+            const float i_z = __ldg(gi + h) + __ldg(pq + h) + __ldg(pt + h);
+            const float i_n = __ldg(gi + 2 * h) + __ldg(pq + 2 * h) + __ldg(pt + 2 * h);
+            float g_r = 0.f, g_z = 0.f, g_n = 0.f, hp = 0.f;
+            if (t > 0) {
+              g_r = sT[rr * TS + lane]; g_z = sT[rr * TS + RU + lane]; g_n = sT[rr * TS + 2 * RU + lane];
+              hp = __ldcg(Hprev + (int64_t)q * 2 * h + enc * h + u);
+              if (GH != nullptr) {                         // recurrent pre-activations (without bias), kept for backward
+                float* gh = GHt + (int64_t)q * 6 * h + enc * 3 * h + u;
+                gh[0] = g_r; gh[h] = g_z; gh[2 * h] = g_n;
+              }
+            }
+            const float r = sigm(i_r + g_r + b_r);
+            const float z = sigm(i_z + g_z + b_z);
+            const float n = tanhf(i_n + r * (g_n + b_n));
+            const float o = (1.f - z) * n + z * hp;
+            Hnext[(int64_t)q * 2 * h + enc * h + u] = o;
+            if (t == __ldg(seq_len + q) - 1) hn[(int64_t)q * h + u] = o;
+          }
+        }
+        __syncthreads();
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();      // the accumulator is re-used by the next tile / step
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    if (t + 1 < max_len && counts.n[t + 1] > 0) grid_barrier(barrier_counter, (unsigned int)(t + 1) * n_ctas);
+    if (t + 1 < max_len && counts.n[t + 1] > 0 && !(dbg & 4)) grid_barrier(barrier_counter, (unsigned int)(t + 1) * n_ctas);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -296,6 +283,10 @@ int launch_gru_recur(const float* GI, const float* PQ, const float* PT, const fl
   if (slices * 2 > sms) return 0;
   StepCounts counts;
   for (int t = 0; t < R_MAX_LEN; ++t) counts.n[t] = t < max_len ? host_batch_sizes[t] : 0;
+  if (const char* dbg = getenv("RENET_DBG_GRU_STEPS")) {   // timing experiments only (results are truncated)
+    const int lim = atoi(dbg);
+    for (int t = lim; t < R_MAX_LEN; ++t) counts.n[t] = 0;
+  }
   RENET_CHECK_CUDA(cudaMemsetAsync(barrier_counter, 0, sizeof(unsigned int), stream));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(slices, 2, gz);
@@ -308,8 +299,10 @@ int launch_gru_recur(const float* GI, const float* PQ, const float* PT, const fl
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int iQ = (int)Q;
+  int dbgf = 0;
+  if (const char* d2 = getenv("RENET_DBG_GRU_FLAGS")) dbgf = atoi(d2);
   RENET_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gru_recur_kernel, GI, PQ, PT, bhh, row_glob, seq_start, seq_len, w_hh4, w_hh3,
-                                      Hs, GH, hn4, hn3, barrier_counter, counts, max_len, iQ, h));
+                                      Hs, GH, hn4, hn3, barrier_counter, counts, max_len, iQ, h, dbgf));
   count_launch();
   return 1;
 }
