@@ -216,33 +216,56 @@ gru_recur_kernel(const float* __restrict__ GI, const float* __restrict__ PQ, con
         if (u < h && !(dbg & 1)) {
           const float b_r = __ldg(bhh + enc * 3 * h + u), b_z = __ldg(bhh + enc * 3 * h + h + u),
                       b_n = __ldg(bhh + enc * 3 * h + 2 * h + u);
-#pragma unroll 4
-          for (int rr = warp; rr < 64; rr += 8) {          // one row per warp per iteration, lane = unit
-            const int q = q0 + half_rows * 64 + rr;
-            if (q >= n_act) break;
-            const int64_t row = (int64_t)__ldg(seq_start + q) + t;
-            const int64_t gl = (int64_t)__ldg(row_glob + row);
-            const float* gi = GI + row * 6 * h + enc * 3 * h + u;
-            const float* pq = PQ + (int64_t)q * 6 * h + enc * 3 * h + u;
-            const float* pt = PT + gl * 6 * h + enc * 3 * h + u;
-            const float i_r = __ldg(gi) + __ldg(pq) + __ldg(pt);
-            const float i_z = __ldg(gi + h) + __ldg(pq + h) + __ldg(pt + h);
-            const float i_n = __ldg(gi + 2 * h) + __ldg(pq + 2 * h) + __ldg(pt + 2 * h);
-            float g_r = 0.f, g_z = 0.f, g_n = 0.f, hp = 0.f;
-            if (t > 0) {
-              g_r = sT[rr * TS + lane]; g_z = sT[rr * TS + RU + lane]; g_n = sT[rr * TS + 2 * RU + lane];
-              hp = __ldcg(Hprev + (int64_t)q * 2 * h + enc * h + u);
-              if (GH != nullptr) {                         // recurrent pre-activations (without bias), kept for backward
-                float* gh = GHt + (int64_t)q * 6 * h + enc * 3 * h + u;
-                gh[0] = g_r; gh[h] = g_z; gh[2 * h] = g_n;
+          // 8 rows per warp and half (row = warp + 8 i), lane = unit.  Index chains (seq_start -> row -> row_glob) are
+          // resolved for all rows first, then the operand loads of 4 rows at a time are in flight together.
+          int64_t rowi[8], gli[8];
+          int qi[8], leni[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            qi[i] = q0 + half_rows * 64 + warp + 8 * i;
+            const int qc = min(qi[i], n_act - 1);
+            rowi[i] = (int64_t)__ldg(seq_start + qc) + t;
+            leni[i] = __ldg(seq_len + qc);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gli[i] = (int64_t)__ldg(row_glob + rowi[i]);
+#pragma unroll
+          for (int b4 = 0; b4 < 8; b4 += 4) {
+            float i_r[4], i_z[4], i_n[4], hp[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int x = b4 + i;
+              const int qc = min(qi[x], n_act - 1);
+              const float* gi = GI + rowi[x] * 6 * h + enc * 3 * h + u;
+              const float* pq = PQ + (int64_t)qc * 6 * h + enc * 3 * h + u;
+              const float* pt = PT + gli[x] * 6 * h + enc * 3 * h + u;
+              i_r[i] = __ldg(gi) + __ldg(pq) + __ldg(pt);
+              i_z[i] = __ldg(gi + h) + __ldg(pq + h) + __ldg(pt + h);
+              i_n[i] = __ldg(gi + 2 * h) + __ldg(pq + 2 * h) + __ldg(pt + 2 * h);
+              hp[i] = t > 0 ? __ldcg(Hprev + (int64_t)qc * 2 * h + enc * h + u) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int x = b4 + i;
+              const int q = qi[x];
+              if (q < n_act) {
+                const int rr = warp + 8 * x;
+                float g_r = 0.f, g_z = 0.f, g_n = 0.f;
+                if (t > 0) {
+                  g_r = sT[rr * TS + lane]; g_z = sT[rr * TS + RU + lane]; g_n = sT[rr * TS + 2 * RU + lane];
+                  if (GH != nullptr) {                     // recurrent pre-activations (without bias), kept for backward
+                    float* gh = GHt + (int64_t)q * 6 * h + enc * 3 * h + u;
+                    gh[0] = g_r; gh[h] = g_z; gh[2 * h] = g_n;
+                  }
+                }
+                const float r = sigm(i_r[i] + g_r + b_r);
+                const float z = sigm(i_z[i] + g_z + b_z);
+                const float n = tanhf(i_n[i] + r * (g_n + b_n));
+                const float o = (1.f - z) * n + z * hp[i];
+                Hnext[(int64_t)q * 2 * h + enc * h + u] = o;
+                if (t == leni[x] - 1) hn[(int64_t)q * h + u] = o;
               }
             }
-            const float r = sigm(i_r + g_r + b_r);
-            const float z = sigm(i_z + g_z + b_z);
-            const float n = tanhf(i_n + r * (g_n + b_n));
-            const float o = (1.f - z) * n + z * hp;
-            Hnext[(int64_t)q * 2 * h + enc * h + u] = o;
-            if (t == __ldg(seq_len + q) - 1) hn[(int64_t)q * h + u] = o;
           }
         }
         __syncthreads();
