@@ -62,7 +62,6 @@ int launch_pack_inputs(const float* H2, const int32_t* readout, const int32_t* r
 int gemm_mode();
 int set_gemm_mode(int m);
 void set_scratch(void* p, int64_t bytes);
-void set_gemm_debug(int d);
 int gather_variant();
 int set_gather_variant(int v);
 
@@ -111,7 +110,6 @@ int64_t renet_launch_count(void) { return g_launches.load(); }
 int renet_set_gemm_engine(int engine) { return set_gemm_mode(engine); }
 int renet_get_gemm_engine(void) { return gemm_mode(); }
 int renet_set_gather_variant(int variant) { return set_gather_variant(variant); }
-int renet_debug_gemm(int flags) { set_gemm_debug(flags); return 0; }
 int renet_set_scratch(void* device_ptr, int64_t bytes) {
   RENET_CHECK_ARG(bytes >= 0 && (device_ptr != nullptr || bytes == 0), "renet_set_scratch: bad arguments");
   set_scratch(device_ptr, bytes);

@@ -11,8 +11,6 @@
 //     recurrent pre-activations GH, which the backward pass re-uses);
 //   * steps are separated by a grid-wide barrier (atomic counter; the launch is cooperative so all CTAs are resident).
 // Outputs match gru.cu's step-by-step path bit-for-bit in layout: Hs [(L+1), Q, 2h], GH [L, Q, 6h], hn4, hn3.
-#include <stdlib.h>
-
 #include <algorithm>
 
 #include "common.cuh"
@@ -56,7 +54,7 @@ gru_recur_kernel(const float* __restrict__ GI, const float* __restrict__ PQ, con
                  const int32_t* __restrict__ seq_start, const int32_t* __restrict__ seq_len,
                  const float* __restrict__ w_hh4, const float* __restrict__ w_hh3, float* __restrict__ Hs,
                  float* __restrict__ GH, float* __restrict__ hn4, float* __restrict__ hn3, unsigned int* barrier_counter,
-                 StepCounts counts, int max_len, int Q, int h, int dbg) {
+                 StepCounts counts, int max_len, int Q, int h) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);
@@ -120,12 +118,10 @@ gru_recur_kernel(const float* __restrict__ GI, const float* __restrict__ PQ, con
     float* GHt = GH + (int64_t)t * Q * 6 * h;
     for (int mt = blockIdx.z; mt < n_mtiles && mt * 128 < n_act; mt += gridDim.z) {
       const int q0 = mt * 128;
-      const int q = q0 + erow;
-      const bool qv = q < n_act && !(dbg & 1);
       // ---- (1) everything that does not depend on the MMAs is fetched first: all K chunks of this tile's h_{t-1} rows
       //          (registers) and the input-projection sums GI[row] + PQ[q] + PT[timestamp] + b_hh of the thread's 16 units
       float4 areg[R_MAX_CHUNKS][4];
-      if (t > 0 && !(dbg & 8)) {
+      if (t > 0) {
 #pragma unroll
         for (int c = 0; c < R_MAX_CHUNKS; ++c) {
 #pragma unroll
@@ -138,7 +134,7 @@ gru_recur_kernel(const float* __restrict__ GI, const float* __restrict__ PQ, con
           }
         }
       }
-      if (t > 0 && !(dbg & 2)) {
+      if (t > 0) {
         // ---- (2) gh = h_{t-1}[tile] @ W_hh_slice^T on the tensor cores: per chunk only split + store + 12 MMAs ----------
 #pragma unroll
         for (int c = 0; c < R_MAX_CHUNKS; ++c) {
@@ -177,7 +173,7 @@ gru_recur_kernel(const float* __restrict__ GI, const float* __restrict__ PQ, con
           }
         }
       }
-      if (t > 0 && !(dbg & 2)) {
+      if (t > 0) {
         mbar_wait(bar0 + 8, mma_phase);
         mma_phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -190,7 +186,7 @@ gru_recur_kernel(const float* __restrict__ GI, const float* __restrict__ PQ, con
       float* sT = reinterpret_cast<float*>(sA);            // [64 rows][100] floats = 25.6 KB
 #pragma unroll 1
       for (int half_rows = 0; half_rows < 2; ++half_rows) {
-        if (t > 0 && !(dbg & 2)) {
+        if (t > 0) {
           if ((erow >> 6) == half_rows) {
 #pragma unroll
             for (int g = 0; g < 3; ++g) {
@@ -213,7 +209,7 @@ gru_recur_kernel(const float* __restrict__ GI, const float* __restrict__ PQ, con
         __syncthreads();
         const int u = u0 + lane;
         float* hn = enc == 0 ? hn4 : hn3;
-        if (u < h && !(dbg & 1)) {
+        if (u < h) {
           const float b_r = __ldg(bhh + enc * 3 * h + u), b_z = __ldg(bhh + enc * 3 * h + h + u),
                       b_n = __ldg(bhh + enc * 3 * h + 2 * h + u);
           // 8 rows per warp and half (row = warp + 8 i), lane = unit.  Index chains (seq_start -> row -> row_glob) are
@@ -274,7 +270,7 @@ gru_recur_kernel(const float* __restrict__ GI, const float* __restrict__ PQ, con
       __syncthreads();      // the accumulator is re-used by the next tile / step
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    if (t + 1 < max_len && counts.n[t + 1] > 0 && !(dbg & 4)) grid_barrier(barrier_counter, (unsigned int)(t + 1) * n_ctas);
+    if (t + 1 < max_len && counts.n[t + 1] > 0) grid_barrier(barrier_counter, (unsigned int)(t + 1) * n_ctas);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -306,10 +302,6 @@ int launch_gru_recur(const float* GI, const float* PQ, const float* PT, const fl
   if (slices * 2 > sms) return 0;
   StepCounts counts;
   for (int t = 0; t < R_MAX_LEN; ++t) counts.n[t] = t < max_len ? host_batch_sizes[t] : 0;
-  if (const char* dbg = getenv("RENET_DBG_GRU_STEPS")) {   // timing experiments only (results are truncated)
-    const int lim = atoi(dbg);
-    for (int t = lim; t < R_MAX_LEN; ++t) counts.n[t] = 0;
-  }
   RENET_CHECK_CUDA(cudaMemsetAsync(barrier_counter, 0, sizeof(unsigned int), stream));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(slices, 2, gz);
@@ -322,10 +314,8 @@ int launch_gru_recur(const float* GI, const float* PQ, const float* PT, const fl
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int iQ = (int)Q;
-  int dbgf = 0;
-  if (const char* d2 = getenv("RENET_DBG_GRU_FLAGS")) dbgf = atoi(d2);
   RENET_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gru_recur_kernel, GI, PQ, PT, bhh, row_glob, seq_start, seq_len, w_hh4, w_hh3,
-                                      Hs, GH, hn4, hn3, barrier_counter, counts, max_len, iQ, h, dbgf));
+                                      Hs, GH, hn4, hn3, barrier_counter, counts, max_len, iQ, h));
   count_launch();
   return 1;
 }

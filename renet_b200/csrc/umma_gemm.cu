@@ -257,7 +257,7 @@ template <bool INDEXED>
 __global__ void __launch_bounds__(UTHREADS, 1)
 umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__ a_index, int64_t lda,
                         const uint8_t* __restrict__ Bp, float* __restrict__ C, int64_t ldc,
-                        const float* __restrict__ bias, int64_t M, int N, int K, int n_chunks, int accumulate, int dbg,
+                        const float* __restrict__ bias, int64_t M, int N, int K, int n_chunks, int accumulate,
                         int64_t batch_a, int64_t batch_bp, int64_t batch_c) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -328,7 +328,7 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
   load_a(0, 0);
   for (int c = 0; c < n_chunks; ++c) {
     const int bs = c & 1;
-    if (tid == 0 && !(dbg & 16)) {   // TMA: one bulk copy per chunk brings the packed B block for BOTH tiles
+    if (tid == 0) {   // TMA: one bulk copy per chunk brings the packed B block for BOTH tiles
       if (c >= 2) mbar_wait(bar0 + 16 + 8 * bs, ((c >> 1) - 1) & 1);          // both tiles' MMAs of chunk c-2 done
       const uint32_t full = bar0 + 8 * bs;
       const uint32_t dstB = smem_base + 4 * P_A_BYTES + bs * P_B_CHUNK;
@@ -345,10 +345,8 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
       float4 v[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) v[t] = vnext[t];
-      if (!(dbg & 2)) {                                                       // next step's global loads fly during this step
-        if (tl == 0) load_a(1, c);
-        else if (c + 1 < n_chunks) load_a(0, c + 1);
-      }
+      if (tl == 0) load_a(1, c);                                              // next step's global loads fly during this step
+      else if (c + 1 < n_chunks) load_a(0, c + 1);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         float4 hi, lo;
@@ -360,7 +358,7 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
       if (tid == 0) {
-        if (tl == 0 && !(dbg & 16)) mbar_wait(bar0 + 8 * bs, (c >> 1) & 1);   // B block landed
+        if (tl == 0) mbar_wait(bar0 + 8 * bs, (c >> 1) & 1);                  // B block landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_hi = smem_base + tl * 2 * P_A_BYTES, a_lo = a_hi + P_A_BYTES;
         const uint32_t b_hi = smem_base + 4 * P_A_BYTES + bs * P_B_CHUNK, b_lo = b_hi + P_B_BYTES;
@@ -370,7 +368,6 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
           const uint32_t ko = ks * 32;                       // 8 fp32 = 32 bytes along the swizzled row
           const uint64_t dAh = make_desc_sw128(a_hi + ko), dAl = make_desc_sw128(a_lo + ko);
           const uint64_t dBh = make_desc_sw128(b_hi + ko), dBl = make_desc_sw128(b_lo + ko);
-          if (dbg & 1) continue;
           umma_tf32(acc, dAh, dBh, idesc, (c | ks) != 0);
           umma_tf32(acc, dAl, dBh, idesc, 1);
           umma_tf32(acc, dAh, dBl, idesc, 1);
@@ -396,7 +393,7 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
       const int64_t gr = row_base + tl * UM + r;
       const uint32_t taddr = tmem_base + tl * 256 + ((uint32_t)(q * 32) << 16);
       auto emit8 = [&](const uint32_t* v8, int cc) {
-        if (gr < M && cc < tile_n && !(dbg & 4)) {
+        if (gr < M && cc < tile_n) {
           float o[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v8[i]);
@@ -453,8 +450,6 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
 
 // Returns 1 if the shape was taken by the tensor-core path (launch enqueued), 0 if the caller should
 // fall back to the FFMA kernel, negative on error.
-static int g_dbg = 0;
-void set_gemm_debug(int d) { g_dbg = d; }
 static uint8_t* g_scratch = nullptr;
 static int64_t g_scratch_bytes = 0;
 void set_scratch(void* p, int64_t bytes) { g_scratch = (uint8_t*)p; g_scratch_bytes = p ? bytes : 0; }
@@ -488,10 +483,10 @@ int umma_gemm_prepacked(const float* A, const int32_t* a_index, int64_t lda, con
   dim3 grid((unsigned)((M + 2 * UM - 1) / (2 * UM)), (unsigned)n_tiles, (unsigned)batch);
   if (a_index)
     umma_gemm_packed_kernel<true><<<grid, UTHREADS, P_SMEM, stream>>>(A, a_index, lda, (const uint8_t*)Bp, C, ldc, bias, M, N, K,
-                                                                    n_chunks, accumulate, g_dbg, batch_a, batch_bp, batch_c);
+                                                                    n_chunks, accumulate, batch_a, batch_bp, batch_c);
   else
     umma_gemm_packed_kernel<false><<<grid, UTHREADS, P_SMEM, stream>>>(A, a_index, lda, (const uint8_t*)Bp, C, ldc, bias, M, N, K,
-                                                                     n_chunks, accumulate, g_dbg, batch_a, batch_bp, batch_c);
+                                                                     n_chunks, accumulate, batch_a, batch_bp, batch_c);
   RENET_CHECK_LAUNCH("umma_gemm_packed_kernel");
   return RENET_OK;
 }
@@ -504,7 +499,7 @@ int umma_gemm_nn_try(const float* A, const int32_t* a_index, int64_t lda, const 
   // ---- packed path: needs the registered scratch buffer for the packed copy of B ---------------------------------
   if (aligned && umma_shape_ok(N, K) && (lda % 4 == 0) && (ldc % 4 == 0) && M >= 64 && g_scratch != nullptr &&
       umma_packed_bytes(N, K) <= g_scratch_bytes && (reinterpret_cast<uintptr_t>(g_scratch) & 127) == 0) {
-    int rc = (g_dbg & 32) ? 0 : umma_pack_b(B, ldb, 1, N, K, g_scratch, 0, stream);
+    int rc = umma_pack_b(B, ldb, 1, N, K, g_scratch, 0, stream);
     if (rc) return rc;
     rc = umma_gemm_prepacked(A, a_index, lda, g_scratch, C, ldc, bias, M, N, K, accumulate, 1, 0, 0, 0, stream);
     return rc ? rc : 1;
