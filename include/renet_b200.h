@@ -238,6 +238,9 @@ int renet_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_gl
  * sizes [10] = {N, E, S, Q, G, max_len, words_used, n_hot_s, n_hot_o, 0}.
  * Returns 0, or 1 when out_capacity < words_used (sizes is filled: grow and call again), <0 on error.
  * ---------------------------------------------------------------------------------------------- */
+/* Threads renet_host_assemble_batch may use per call (default 8; use 1 when many calls run concurrently, e.g.
+ * from a prefetching loader).  Returns the previous value. */
+int renet_set_host_threads(int n);
 int renet_host_assemble_batch(
     int64_t T, const int64_t* g_node_off, const int32_t* g_node_ent, const int64_t* g_edge_off,
     const int32_t* g_src, const int32_t* g_dst, const int32_t* g_type_s, const int32_t* g_type_o,

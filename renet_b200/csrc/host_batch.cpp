@@ -24,11 +24,13 @@ void set_error(const char* fmt, ...);
 }
 
 namespace {
+std::atomic<int> g_host_threads{8};
 // components are independent: a handful of short-lived threads pull component indices from a counter
 template <class F>
 void parallel_for(int64_t n, F f) {
   unsigned hw = std::thread::hardware_concurrency();
-  const int nt = (int)std::min<int64_t>(std::min<unsigned>(hw ? hw : 1, 8), (n + 15) / 16);
+  const int cap = std::max(1, g_host_threads.load());
+  const int nt = (int)std::min<int64_t>(std::min<unsigned>(hw ? hw : 1, (unsigned)cap), (n + 15) / 16);
   if (nt <= 1) { for (int64_t i = 0; i < n; ++i) f(i); return; }
   std::atomic<int64_t> next{0};
   auto work = [&]() { for (int64_t i = next.fetch_add(4); i < n; i = next.fetch_add(4)) for (int64_t j = i; j < std::min(n, i + 4); ++j) f(j); };
@@ -38,6 +40,12 @@ void parallel_for(int64_t n, F f) {
   for (auto& t : th) t.join();
 }
 }  // namespace
+
+extern "C" int renet_set_host_threads(int n) {
+  const int prev = g_host_threads.load();
+  g_host_threads.store(n < 1 ? 1 : n);
+  return prev;
+}
 
 extern "C" int renet_host_assemble_batch(
     // ---- graph store ------------------------------------------------------------------------------

@@ -241,13 +241,16 @@ def assemble_view(view, device, sort=True):
     return hb
 
 
-def prefetch(view_groups, device, depth=2, workers=4, sort=True):
+def prefetch(view_groups, device, depth=2, workers=4, sort=True, inner_threads=None):
     """Pipeline the host batching: ``view_groups`` is an iterable of tuples of HistoryViews (one tuple per step,
     e.g. (subject view, object view)); yields tuples of HistoryBatches on ``device``.  While the consumer runs
     step i on the GPU, worker threads run the C++ batcher (which releases the GIL) for steps i+1 .. i+depth into
     their own pinned staging buffers; the H2D copy is issued from the consumer's thread on its current stream."""
     import collections
     from concurrent.futures import ThreadPoolExecutor
+    prev_threads = None
+    if inner_threads is not None:          # many concurrent batcher calls: fewer threads inside each
+        prev_threads = _lib.lib().renet_set_host_threads(int(inner_threads))
     free = collections.deque()
     pending = collections.deque()
     it = iter(view_groups)
@@ -280,3 +283,5 @@ def prefetch(view_groups, device, depth=2, workers=4, sort=True):
             while in_flight and (in_flight[0][0] is None or in_flight[0][0].query()):
                 free.append(in_flight.popleft()[1])
             yield tuple(out)
+    if prev_threads is not None:
+        _lib.lib().renet_set_host_threads(prev_threads)
