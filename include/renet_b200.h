@@ -232,7 +232,8 @@ int renet_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_gl
  *   node_ent[N] row_ptr[N+1] col_src[E] col_type_s[E] col_type_o[E] norm[N](float bits)
  *   readout[S] row_comp[S] row_seq[S] seq_start[Q] seq_len[Q] packed_row[S]
  *   comp_ptr[G+1] comp_order[G] rel_slot_s[R2] hot_s[n_hot_max] rel_slot_o[R2] hot_o[n_hot_max]
- * (the last line feeds renet_rgcn_gather_comp: components largest-first, and the n_hot_max most frequent
+ *   s_idx[B] comp_graph[G]
+ * (the comp/rel line feeds renet_rgcn_gather_comp: components largest-first, and the n_hot_max most frequent
  * edge types of the batch for each type column).  comp_graph_out [G] (graph index of every component,
  * first-appearance order), batch_sizes_out [max_len],
  * sizes [10] = {N, E, S, Q, G, max_len, words_used, n_hot_s, n_hot_o, 0}.

@@ -16,7 +16,7 @@ from torch.nn.utils.rnn import PackedSequence
 
 from . import _lib
 from .rgcn import RGCNBlockLayer as RGCNLayer
-from .utils import assemble_history_batch, global_rows
+from .utils import assemble_history_batch, global_rows, global_rows_of_batch
 
 
 class _PackInputsFn(torch.autograd.Function):
@@ -98,7 +98,7 @@ class RGCNAggregator(nn.Module):
         return self.rgcn2.apply_layer(g, H1, None, reverse)
 
     def _sorted_ids(self, hb, s, r, device):
-        idx = torch.from_numpy(hb.s_idx).to(device)
+        idx = hb.sample_order(device)
         s_tem, r_tem = s.reshape(-1)[idx], r.reshape(-1)[idx]
         Q = hb.num_seq
         return s_tem, r_tem, s_tem[:Q].to(torch.int32).contiguous(), r_tem[:Q].to(torch.int32).contiguous()
@@ -137,7 +137,7 @@ class RGCNAggregator(nn.Module):
         dev = ent_embeds.device
         hb = self._batch(hist, s, graph_dict, dev, True)
         H2 = self.aggregate(hb, ent_embeds, reverse)
-        glob = global_rows(global_emb, hb.times, self.h_dim, dev)
+        glob = global_rows_of_batch(global_emb, hb, self.h_dim, dev)
         _, _, seq_s, seq_r = self._sorted_ids(hb, s, r, dev)
         s_h, s_q = fused_gru(H2, ent_embeds, rel_embeds, glob, hb, seq_s, seq_r, encoder, encoder_r)
         return s_h, s_q, hb

@@ -139,7 +139,8 @@ extern "C" int renet_host_assemble_batch(
   //  node_ent[N] row_ptr[N+1] col_src[E] col_type_s[E] col_type_o[E] norm[N](f32 bits)
   //  readout[S] row_comp[S] row_seq[S] seq_start[Q] seq_len[Q] packed_row[S]
   //  comp_ptr[G+1] comp_order[G] rel_slot_s[R2] hot_s[n_hot_max] rel_slot_o[R2] hot_o[n_hot_max]
-  const int64_t words = N + (N + 1) + 3 * E + N + 3 * S + 2 * Q + S + (G + 1) + G + 2 * (int64_t)(R2 + n_hot_max);
+  //  s_idx[B] comp_graph[G]      (device copies of the two small host outputs, so no separate H2D is needed)
+  const int64_t words = N + (N + 1) + 3 * E + N + 3 * S + 2 * Q + S + (G + 1) + G + 2 * (int64_t)(R2 + n_hot_max) + B + G;
   sizes[0] = N; sizes[1] = E; sizes[4] = G; sizes[6] = words;
   if (words > out_capacity) return 1;   // caller grows the staging buffer and retries
   int32_t* o_node = out;
@@ -224,5 +225,9 @@ extern "C" int renet_host_assemble_batch(
     for (int32_t i = nh; i < n_hot_max; ++i) hot[i] = 0;
     sizes[7 + w] = nh;
   }
+  int32_t* o_sidx = o_hot + 2 * (R2 + n_hot_max);
+  for (int64_t i = 0; i < B; ++i) o_sidx[i] = (int32_t)s_idx_out[i];
+  int32_t* o_cg = o_sidx + B;
+  for (int64_t c = 0; c < G; ++c) o_cg[c] = comp_graph[c];
   return RENET_OK;
 }

@@ -163,7 +163,7 @@ def assemble_view_raw(view, out, sort=True):
     _lib.check(rc, 'renet_host_assemble_batch')
     N, E, S, Q, G, max_len, words = (int(x) for x in sizes[:7])
     return dict(N=N, E=E, S=S, Q=Q, G=G, max_len=max_len, words=words, s_idx=s_idx, comp_graph=comp_graph[:G],
-                batch_sizes=bsz[:max_len].copy(), R2=gs.num_types, n_hot_s=int(sizes[7]), n_hot_o=int(sizes[8]))
+                batch_sizes=bsz[:max_len].copy(), R2=gs.num_types, n_hot_s=int(sizes[7]), n_hot_o=int(sizes[8]), B=B)
 
 
 def split_raw(buf, r):
@@ -174,7 +174,8 @@ def split_raw(buf, r):
     for name, n in (('node_ent', N), ('row_ptr', N + 1), ('col_src', E), ('col_type_s', E), ('col_type_o', E),
                     ('norm', N), ('readout', S), ('row_comp', S), ('row_seq', S), ('seq_start', Q), ('seq_len', Q),
                     ('packed_row', S), ('comp_ptr', r['G'] + 1), ('comp_order', r['G']), ('rel_slot_s', r['R2']),
-                    ('hot_s', N_HOT), ('rel_slot_o', r['R2']), ('hot_o', N_HOT)):
+                    ('hot_s', N_HOT), ('rel_slot_o', r['R2']), ('hot_o', N_HOT), ('s_idx', r['B']),
+                    ('comp_graph', r['G'])):
         out[name] = buf[o:o + n]
         o += n
     return out
@@ -224,6 +225,8 @@ def _upload(view, buf, r, device):
     hb.batch_sizes = r['batch_sizes']
     hb.times = view.store.gs.times[r['comp_graph']]
     hb.h2d_bytes = words * 4
+    hb.s_idx_dev, hb.comp_graph_dev = d['s_idx'], d['comp_graph']     # device copies: no pageable H2D later
+    hb.graph_store = view.store.gs
     return hb, ev
 
 

@@ -78,7 +78,7 @@ class RENet(nn.Module):
             # the reference drops out the GRU inputs (Aggregator.py:157-158); the fused path has no
             # materialised input to drop, so training with dropout goes through forward_unfused().
             raise RuntimeError('fused encode() does not implement input dropout; use dropout=0 or forward_unfused')
-        idx = torch.from_numpy(hb.s_idx).to(triplets.device)
+        idx = hb.sample_order(triplets.device)
         pad = torch.zeros(len(s) - s_h.shape[0], self.h_dim, device=s_h.device)
         s_h = torch.cat((s_h, pad), dim=0)                                # model.py:88
         s_q = torch.cat((s_q, pad), dim=0)                                # model.py:96

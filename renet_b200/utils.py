@@ -17,7 +17,15 @@ from .graph import BatchedHistoryGraph, HistoryGraph, as_history_graph, get_big_
 class HistoryBatch:
     """Everything the aggregator needs for one direction of one batch."""
     __slots__ = ('s_idx', 'seq_len', 'num_seq', 'times', 'graph', 'readout', 'readout_host', 'row_glob',
-                 'row_seq', 'seq_start', 'packed_row', 'batch_sizes', 'S', 'h2d_bytes')
+                 'row_seq', 'seq_start', 'packed_row', 'batch_sizes', 'S', 'h2d_bytes', 's_idx_dev', 'comp_graph_dev',
+                 'graph_store')
+
+    def sample_order(self, device):
+        """device int64 index of the samples in processing order (history length descending)."""
+        dev_idx = getattr(self, 's_idx_dev', None)
+        if dev_idx is not None:
+            return dev_idx.long()
+        return torch.from_numpy(self.s_idx).to(device)
 
 
 def _history_order(hist_len, sort):
@@ -171,10 +179,19 @@ def upload_history_batch(hb, device):
 _GLOB_CACHE = {}
 
 
-def global_rows(global_emb, times, h, device):
-    """[T,h] matrix of global_emb[t] for the batch's distinct timestamps.  The reference gathers one row per
-    read-out row with a .cpu() each (utils.py:224-225); here the dict is turned into a dense device table
-    once (cached per dict object) and a batch is one index_select."""
+def global_rows_of_batch(global_emb, hb, h, device):
+    """global_rows for a HistoryBatch; when the batch came from the C++ batcher its component -> graph index is
+    already on the device and the table is indexed without any host->device copy."""
+    cg = getattr(hb, 'comp_graph_dev', None)
+    gs = getattr(hb, 'graph_store', None)
+    if cg is not None and gs is not None:
+        table, keys = _global_table(global_emb, h, device)
+        if len(keys) == len(gs.times) and (keys is gs.times or np.array_equal(keys, gs.times)):
+            return table[cg.long()]
+    return global_rows(global_emb, hb.times, h, device)
+
+
+def _global_table(global_emb, h, device):
     key = id(global_emb)
     hit = _GLOB_CACHE.get(key)
     if hit is None or hit[0] is not global_emb or hit[1] != len(global_emb) or hit[3].device != torch.device(device):
@@ -183,8 +200,16 @@ def global_rows(global_emb, times, h, device):
         hit = (global_emb, len(global_emb), keys, table.view(len(keys), h))
         _GLOB_CACHE.clear()
         _GLOB_CACHE[key] = hit
-    idx = np.searchsorted(hit[2], np.asarray(times, dtype=np.int64))
-    return hit[3][torch.from_numpy(idx).to(device)]
+    return hit[3], hit[2]
+
+
+def global_rows(global_emb, times, h, device):
+    """[T,h] matrix of global_emb[t] for the batch's distinct timestamps.  The reference gathers one row per
+    read-out row with a .cpu() each (utils.py:224-225); here the dict is turned into a dense device table
+    once (cached per dict object) and a batch is one index_select."""
+    table, keys = _global_table(global_emb, h, device)
+    idx = np.searchsorted(keys, np.asarray(times, dtype=np.int64))
+    return table[torch.from_numpy(idx).to(device)]
 
 
 def _wrap(hb, s, r, ent_embeds, global_emb):

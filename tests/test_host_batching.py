@@ -138,6 +138,8 @@ def test_cpp_batcher_matches_numpy_path():
             np.testing.assert_array_equal(got[k], np.asarray(v).astype(np.int32), err_msg=k)
         np.testing.assert_array_equal(r['batch_sizes'], hb.batch_sizes)
         np.testing.assert_array_equal(gs.times[r['comp_graph']], hb.times)
+        np.testing.assert_array_equal(got['s_idx'], hb.s_idx)
+        np.testing.assert_array_equal(got['comp_graph'], r['comp_graph'])
         ex = utils.component_extras(np.concatenate(([0], np.cumsum(g['comp_sizes']))),
                                     np.bincount(np.searchsorted(np.cumsum(g['comp_sizes']), np.repeat(np.arange(len(g['node_ent'])), np.diff(g['row_ptr'])), side='right'), minlength=len(g['comp_sizes'])),
                                     g['col_type_s'], g['col_type_o'], num_types=gs.num_types)
