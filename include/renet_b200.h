@@ -251,6 +251,22 @@ int renet_host_assemble_batch(
     int64_t* s_idx_out, int32_t* out, int64_t out_capacity, int32_t* comp_graph_out,
     int32_t* batch_sizes_out, int32_t max_len_capacity, int64_t* sizes);
 
+/* One call for the whole forward hot path of one direction (inference / no autograd):
+ *   H1 = relu-layer(ent[node_ent]), H2 = linear-layer(H1)   (renet_rgcn_block_fwd x2, Aggregator.py:136-137)
+ *   hn4, hn3 = renet_gru_fwd(H2, ...)                          (Aggregator.py:139-165 + model.py:86,94)
+ * Same arguments as the individual entry points; H1/H2 [N,h] are caller-provided outputs. */
+int renet_encode_fwd(const float* ent, const int32_t* node_ent, const int32_t* row_ptr, const int32_t* col_src,
+                     const int32_t* col_type, const float* norm,
+                     const float* W1, const float* Wloop1, const float* W2, const float* Wloop2,
+                     float* H1, float* H2, int64_t N, int64_t E, int32_t R2,
+                     const int32_t* readout, const int32_t* row_glob, const float* glob, const float* rel,
+                     const int32_t* seq_s, const int32_t* seq_r, const int32_t* seq_len, const int32_t* seq_start,
+                     const int32_t* host_batch_sizes, int32_t max_len,
+                     const float* w_ih4, const float* w_hh4, const float* b_ih4, const float* b_hh4,
+                     const float* w_ih3, const float* w_hh3, const float* b_ih3, const float* b_hh3,
+                     float* hn4, float* hn3, int64_t S, int64_t Q, int64_t T, int32_t h, int32_t num_bases,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Materialise the packed GRU inputs exactly as the reference's aggregator returns them
  * (PackedSequence.data, time-major: Aggregator.py:160-165):  X4 [S,4h], X3 [S,3h];
  * packed_row [S] maps packed position -> sequence-major row. */

@@ -37,6 +37,8 @@ SIGNATURES = {
     'renet_gru_bwd': (ctypes.c_int, [_vp] * 11 + [_i32] + [_vp] * 18 + [_i64, _i64, _i64, _i64, _i32, _vp, _vp, _i64, _vp]),
     'renet_set_host_threads': (ctypes.c_int, [ctypes.c_int]),
     'renet_host_assemble_batch': (ctypes.c_int, [_i64] + [_vp] * 13 + [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
+    'renet_encode_fwd': (ctypes.c_int, [_vp] * 12 + [_i64, _i64, _i32] + [_vp] * 9 + [_i32] + [_vp] * 10 +
+                         [_i64, _i64, _i64, _i32, _i32, _vp, _i64, _vp]),
     'renet_pack_inputs': (ctypes.c_int, [_vp] * 12 + [_i64, _i32, _vp]),
 }
 

@@ -136,8 +136,42 @@ class RGCNAggregator(nn.Module):
         from .gru import fused_gru
         dev = ent_embeds.device
         hb = self._batch(hist, s, graph_dict, dev, True)
+        if not torch.is_grad_enabled() and not self.training:
+            return self._encode_inference(hb, s, r, ent_embeds, rel_embeds, global_emb, reverse, encoder, encoder_r)
         H2 = self.aggregate(hb, ent_embeds, reverse)
         glob = global_rows_of_batch(global_emb, hb, self.h_dim, dev)
         _, _, seq_s, seq_r = self._sorted_ids(hb, s, r, dev)
         s_h, s_q = fused_gru(H2, ent_embeds, rel_embeds, glob, hb, seq_s, seq_r, encoder, encoder_r)
         return s_h, s_q, hb
+
+    def _encode_inference(self, hb, s, r, ent_embeds, rel_embeds, global_emb, reverse, encoder, encoder_r):
+        """No-autograd fast path: the whole direction (2 RGCN layers + read-out + both GRUs) is ONE C-ABI call
+        (renet_encode_fwd), so the Python cost per direction is a handful of tensor ops instead of ~60."""
+        from .gru import _gru_params
+        L = _lib.lib()
+        dev = ent_embeds.device
+        g, h = hb.graph, self.h_dim
+        glob = global_rows_of_batch(global_emb, hb, h, dev)
+        idx = hb.sample_order(dev)
+        Q = hb.num_seq
+        seq_s = s.reshape(-1)[idx][:Q].to(torch.int32)
+        seq_r = r.reshape(-1)[idx][:Q].to(torch.int32)
+        p4, p3 = _gru_params(encoder), _gru_params(encoder_r)
+        rel = rel_embeds.contiguous()
+        T = glob.shape[0]
+        H = torch.empty(2, g.N, h, device=dev)
+        hn = torch.zeros(2, Q, h, device=dev)
+        nbytes = int(L.renet_gru_workspace_bytes(hb.S, Q, T, h))
+        ws = torch.empty(nbytes // 4 + 4, dtype=torch.float32, device=dev)
+        bs = hb.batch_sizes
+        P = _lib.ptr
+        l1, l2 = self.rgcn1, self.rgcn2
+        rc = L.renet_encode_fwd(P(ent_embeds), P(g.node_ent), P(g.row_ptr), P(g.col_src), P(g.col_type(reverse)),
+                                P(g.norm), P(l1.weight), P(l1.loop_weight), P(l2.weight), P(l2.loop_weight), P(H[0]),
+                                P(H[1]), g.N, g.E, l1.weight.shape[0], P(hb.readout), P(hb.row_glob), P(glob), P(rel),
+                                P(seq_s), P(seq_r), P(g.seq_len_dev), P(hb.seq_start),
+                                bs.ctypes.data_as(_lib.ctypes.c_void_p), len(bs), P(p4[0]), P(p4[1]), P(p4[2]), P(p4[3]),
+                                P(p3[0]), P(p3[1]), P(p3[2]), P(p3[3]), P(hn[0]), P(hn[1]), hb.S, Q, T, h, l1.num_bases,
+                                P(ws), nbytes, _lib.stream())
+        _lib.check(rc, 'renet_encode_fwd')
+        return hn[0], hn[1], hb

@@ -307,6 +307,27 @@ int renet_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_gl
                         (float*)bwd_workspace, (cudaStream_t)stream);
 }
 
+int renet_encode_fwd(const float* ent, const int32_t* node_ent, const int32_t* row_ptr, const int32_t* col_src,
+                     const int32_t* col_type, const float* norm, const float* W1, const float* Wloop1, const float* W2,
+                     const float* Wloop2, float* H1, float* H2, int64_t N, int64_t E, int32_t R2, const int32_t* readout,
+                     const int32_t* row_glob, const float* glob, const float* rel, const int32_t* seq_s,
+                     const int32_t* seq_r, const int32_t* seq_len, const int32_t* seq_start,
+                     const int32_t* host_batch_sizes, int32_t max_len, const float* w_ih4, const float* w_hh4,
+                     const float* b_ih4, const float* b_hh4, const float* w_ih3, const float* w_hh3, const float* b_ih3,
+                     const float* b_hh3, float* hn4, float* hn3, int64_t S, int64_t Q, int64_t T, int32_t h,
+                     int32_t num_bases, void* workspace, int64_t workspace_bytes, void* stream) {
+  // layer 1 (embedding lookup fused through node_ent, ReLU), layer 2 (linear), then read-out + both GRUs
+  int rc = renet_rgcn_block_fwd(ent, node_ent, W1, Wloop1, row_ptr, col_src, col_type, norm, H1, N, E, h, h, num_bases, R2,
+                                1, stream);
+  if (rc) return rc;
+  rc = renet_rgcn_block_fwd(H1, nullptr, W2, Wloop2, row_ptr, col_src, col_type, norm, H2, N, E, h, h, num_bases, R2, 0,
+                            stream);
+  if (rc) return rc;
+  return renet_gru_fwd(H2, readout, row_glob, glob, ent, rel, seq_s, seq_r, seq_len, seq_start, host_batch_sizes, max_len,
+                       w_ih4, w_hh4, b_ih4, b_hh4, w_ih3, w_hh3, b_ih3, b_hh3, hn4, hn3, S, Q, T, h, workspace,
+                       workspace_bytes, stream);
+}
+
 int renet_pack_inputs(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
                       const float* ent, const float* rel, const int32_t* row_seq, const int32_t* seq_s,
                       const int32_t* seq_r, const int32_t* packed_row, float* X4, float* X3, int64_t S, int32_t h,
