@@ -142,6 +142,7 @@ class _Staging:
 
 
 _staging = {}
+_PINNED_POOL = __import__('collections').deque()
 
 
 def assemble_view_raw(view, out, sort=True):
@@ -254,12 +255,16 @@ def prefetch(view_groups, device, depth=2, workers=4, sort=True, inner_threads=N
     prev_threads = None
     if inner_threads is not None:          # many concurrent batcher calls: fewer threads inside each
         prev_threads = _lib.lib().renet_set_host_threads(int(inner_threads))
-    free = collections.deque()
+    free = _PINNED_POOL          # pinned staging buffers are expensive to create (~4 ms each): pooled per process
     pending = collections.deque()
     it = iter(view_groups)
 
     def job(view):
-        holder = [free.pop() if free else torch.empty(1 << 21, dtype=torch.int32).pin_memory()]
+        try:
+            buf = free.pop()
+        except IndexError:
+            buf = torch.empty(1 << 21, dtype=torch.int32).pin_memory()
+        holder = [buf]
         return view, holder, _stage(view, holder, sort)
 
     with ThreadPoolExecutor(max_workers=workers) as pool:
@@ -286,5 +291,9 @@ def prefetch(view_groups, device, depth=2, workers=4, sort=True, inner_threads=N
             while in_flight and (in_flight[0][0] is None or in_flight[0][0].query()):
                 free.append(in_flight.popleft()[1])
             yield tuple(out)
+        for ev, buf in in_flight:          # hand the remaining buffers back once their copies have completed
+            if ev is not None:
+                ev.synchronize()
+            free.append(buf)
     if prev_threads is not None:
         _lib.lib().renet_set_host_threads(prev_threads)
