@@ -257,6 +257,66 @@ def gen_renet_icews18_slice(ns):
     print('renet_icews18_slice.npz: loss', res['subj/loss'], res['obj/loss'], 'quads', len(quads))
 
 
+def gen_renet_eval_tiny(ns):
+    """Test-time path (model.py:107-446) of the reference on the tiny TKG: init_history, filtered + raw ranks at the
+    first test timestamp (no roll-over), then the roll-over to the second test timestamp (sampling from a stub global
+    model, predicted graph, history roll) and the ranks after it."""
+    from oracle import restate
+    from oracle.stub_global import StubGlobalModel
+    blob = np.load(os.path.join(OUT, 'renet_tiny.npz'))
+    quads = blob['quads'].astype(np.int64)
+    num_e, R, h, nb, seed = int(blob['num_e']), int(blob['R']), int(blob['h']), int(blob['nb']), 21
+    times = np.unique(quads[:, 3])
+    t_valid, t_test = times[-4], times[-2]
+    S, ST, O, OT = restate.build_history(quads, num_e)
+    split = lambda lo, hi: np.flatnonzero((quads[:, 3] >= lo) & (quads[:, 3] < hi))   # noqa: E731
+    tr, va, te = split(0, t_valid), split(t_valid, t_test), split(t_test, times[-1] + 1)
+    pick = lambda L, idx: [L[i] for i in idx]                                           # noqa: E731
+    with ref_loader.cpu_patches():
+        gd = {int(t): ns.utils.get_big_graph(quads[quads[:, 3] == t][:, :3], R) for t in times}
+        m = ns.model.RENet(num_e, h, R, dropout=0, model=0, seq_len=10, num_k=5)
+        m.aggregator = ns.Aggregator.RGCNAggregator(h, 0, num_e, R, nb, 0, 10)
+        m.load_state_dict(det_params(RENET_SHAPES(num_e, h, R, nb), seed), strict=True)
+        m.eval()
+        m.global_emb = det_global_emb(times, h, seed + 1)
+        m.graph_dict = gd
+        m.init_history(quads[tr], (pick(S, tr), pick(ST, tr)), (pick(O, tr), pick(OT, tr)),
+                       quads[va], (pick(S, va), pick(ST, va)), (pick(O, va), pick(OT, va)),
+                       quads[te], (pick(S, te), pick(ST, te)), (pick(O, te), pick(OT, te)))
+        res = {'hist_len_s': np.array([len(x) for x in m.s_hist_test]), 'hist_len_o': np.array([len(x) for x in m.o_hist_test]),
+               'hist_last_t_s': np.array([x[-1] if len(x) else -1 for x in m.s_hist_test_t])}
+        m.latest_time = torch.tensor(int(t_test))
+        gm = StubGlobalModel(num_e, h, seed + 2)
+        allq = torch.from_numpy(quads)
+        torch.manual_seed(1234)
+        out = {k: [] for k in ('raw', 'filt', 'loss', 'sub_pred', 'ob_pred')}
+        with torch.no_grad():
+            for i in te:
+                trip = torch.from_numpy(quads[i])
+                sh, oh = (S[i], ST[i]), (O[i], OT[i])
+                rolled = int(trip[3]) != int(m.latest_time)
+                fr, loss = m.evaluate_filter(trip, sh, oh, gm, allq)
+                if rolled:
+                    res['rolled_at'] = np.int64(i)
+                    res['after_len_s'] = np.array([len(x) for x in m.s_hist_test])
+                    res['after_len_o'] = np.array([len(x) for x in m.o_hist_test])
+                    rows = [np.concatenate([[e], r]) for e in range(num_e) if len(m.s_hist_test_t[e]) and m.s_hist_test_t[e][-1] == int(t_test)
+                            and len(m.s_hist_test[e]) for r in np.asarray(m.s_hist_test[e][-1]).reshape(-1, 2)]
+                    res['after_new_s_rows'] = np.unique(np.asarray(rows, dtype=np.int64).reshape(-1, 3), axis=0)
+                    g = m.graph_dict[int(t_test)]
+                    res['pred_graph_nodes'] = np.sort(g.ndata['id'].view(-1).numpy())
+                    res['pred_graph_num_edges'] = np.int64(g.number_of_edges())
+                rr, _ = m.evaluate(trip, sh, oh, gm)
+                _, sp, op = m.predict(trip, sh, oh, gm)
+                out['raw'].append(rr); out['filt'].append(fr); out['loss'].append(loss.item())
+                out['sub_pred'].append(sp.numpy().copy()); out['ob_pred'].append(op.numpy().copy())
+    res.update({k: np.asarray(v) for k, v in out.items()})
+    res.update(tr=tr, va=va, te=te, seed=seed, num_k=5, gm_calls=np.asarray(gm.calls, dtype=np.int64))
+    np.savez_compressed(os.path.join(OUT, 'renet_eval_tiny.npz'), **res)
+    print('renet_eval_tiny.npz: %d test triples, rolled at %s, mean filt rank %.2f, calls %d' % (
+        len(te), res.get('rolled_at'), res['filt'].mean(), len(gm.calls)))
+
+
 def gen_graph_kats(ns):
     """utils.get_big_graph / make_subgraph / get_sorted_s_r_embed_rgcn structure on a tiny stream."""
     from oracle import restate
@@ -295,3 +355,4 @@ if __name__ == '__main__':
     gen_graph_kats(ns)
     gen_renet_tiny(ns)
     gen_renet_icews18_slice(ns)
+    gen_renet_eval_tiny(ns)

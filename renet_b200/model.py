@@ -7,8 +7,9 @@ o_hist, graph_dict, subject=True) -> loss`` follows model.py:64-104: direction s
 history length, RGCN aggregate, GRU final hidden, zero rows for empty histories, the two linear
 decoders + cross-entropy (decoders stay PyTorch: SURVEY.md section 8(f) row 3).
 
-Scope of this class is the training forward of the hot path; the test-time autoregressive routines
-(model.py:107-446) are out of scope this round.
+The test-time autoregressive routines (model.py:107-446: ``init_history``, ``pred_r_rank2``,
+``predict``, ``evaluate``, ``evaluate_filter``, ``update_cache``) come from ``inference.RENetInference``
+ and run on the same kernels.
 """
 from collections import defaultdict
 
@@ -16,9 +17,10 @@ import torch
 import torch.nn as nn
 
 from .aggregator import RGCNAggregator
+from .inference import RENetInference
 
 
-class RENet(nn.Module):
+class RENet(RENetInference, nn.Module):
     def __init__(self, in_dim, h_dim, num_rels, dropout=0, model=0, seq_len=10, num_k=10, num_bases=100):
         super(RENet, self).__init__()
         self.in_dim = in_dim

@@ -1,0 +1,56 @@
+"""not gpu: host logic of the test-time path (renet_b200/inference.py) against the reference's golden run.
+
+The CUDA encode is replaced by the CPU oracle here (tests may do that; the product may not), so what this pins is
+init_history, the roll-over control flow (sampling, candidate selection, caches, predicted graph, history roll), the
+decoders and the rank rules.  tests/test_gpu_inference.py runs the same flow on the kernels."""
+import numpy as np
+import torch
+
+from helpers import check_eval_against_golden, eval_flow, eval_setup
+from oracle import restate
+
+
+def _plain(g):
+    if isinstance(g, restate.PlainGraph):
+        return g
+    src, dst, ts, to = g._coo
+    return restate.PlainGraph(g.node_id, src.astype(np.int64), dst.astype(np.int64), ts.astype(np.int64), to.astype(np.int64))
+
+
+def _oracle_encode(ctx):
+    params, (num_e, R, h, nb) = ctx['params'], ctx['dims']
+
+    def encode(hist, s, r, ent_embeds, rel_embeds, graph_dict, global_emb, reverse, encoder, encoder_r):
+        s, r = np.asarray(s.cpu()).reshape(-1), np.asarray(r.cpu()).reshape(-1)
+        z = np.zeros_like(s)
+        tr = np.stack((z, r, s), 1) if reverse else np.stack((s, r, z), 1)
+        gd = {t: _plain(g) for t, g in graph_dict.items()}
+        out = restate.renet_forward(params, tr, hist[0], hist[1], gd, global_emb, not reverse, R, nb)
+        assert np.array_equal(out['batch'].s_idx, np.arange(len(s)))     # equal lengths: stable sort = identity
+        return out['s_h'], out['s_q'], None
+    return encode
+
+
+def test_rank_rule_and_cache_update():
+    from renet_b200.inference import history_triples, rank_with_ties
+    sc = torch.tensor([0.5, 0.9, 0.5, 0.1, 0.5])
+    assert rank_with_ties(sc, 1) == 1 and rank_with_ties(sc, 3) == 5
+    assert rank_with_ties(sc, 0) == 1 + (3 - 1) / 2 + 1                  # model.py:373-379 tie rule
+    from renet_b200.model import RENet
+    m = RENet(10, 4, 3, num_bases=2)
+    c = m.update_cache([], torch.tensor(2), torch.tensor([[3], [13]]))   # % in_dim (model.py:422)
+    assert c.tolist() == [[2, 3], [2, 3]]
+    c = m.update_cache(torch.tensor([[2, 3], [1, 4]]), torch.tensor(2), torch.tensor([[3], [5]]))
+    assert c.tolist() == [[2, 3], [1, 4], [2, 5]]
+    c = m.update_cache(torch.tensor([[1, 4]]), torch.tensor(2), torch.tensor([[4]]))
+    assert c.tolist() == [[1, 4], [2, 4]]
+    s_cache = [[] for _ in range(10)]; o_cache = [[] for _ in range(10)]
+    s_cache[1] = torch.tensor([[2, 5]]); o_cache[5] = torch.tensor([[2, 1], [0, 7]])
+    assert history_triples(s_cache, o_cache).tolist() == [[1, 2, 5], [7, 0, 5]]   # utils.py:95-113
+
+
+def test_eval_flow_matches_reference_golden_with_oracle_encode():
+    ctx = eval_setup('cpu')
+    ctx['model'].aggregator.encode = _oracle_encode(ctx)
+    res = eval_flow(ctx, 'cpu')
+    check_eval_against_golden(res, ctx['ev'])
