@@ -8,6 +8,8 @@ destination-sorted per-timestamp edge lists (so the batched graph is born in CSR
 everything reaches the GPU in two pinned copies.  Nothing here touches ``.item()`` per element or
 does per-row device copies (the reference does S of them, utils.py:225).
 """
+import operator
+
 import numpy as np
 import torch
 
@@ -192,12 +194,16 @@ def global_rows_of_batch(global_emb, hb, h, device):
 
 
 def _global_table(global_emb, h, device):
+    """Dense [T,h] device table of the dict, cached per dict object.  The cache is dropped when the dict grows OR when
+    any value object is replaced (the test-time roll-over overwrites global_emb[latest_time], model.py:302-303)."""
     key = id(global_emb)
     hit = _GLOB_CACHE.get(key)
-    if hit is None or hit[0] is not global_emb or hit[1] != len(global_emb) or hit[3].device != torch.device(device):
+    vals = list(global_emb.values())
+    if (hit is None or hit[0] is not global_emb or len(hit[1]) != len(vals) or hit[3].device != torch.device(device)
+            or not all(map(operator.is_, vals, hit[1]))):
         keys = np.asarray(sorted(int(t) for t in global_emb.keys()), dtype=np.int64)
         table = torch.stack([global_emb[int(t)].reshape(-1) for t in keys]).to(device=device, dtype=torch.float32)
-        hit = (global_emb, len(global_emb), keys, table.view(len(keys), h))
+        hit = (global_emb, vals, keys, table.view(len(keys), h))
         _GLOB_CACHE.clear()
         _GLOB_CACHE[key] = hit
     return hit[3], hit[2]
