@@ -48,6 +48,7 @@ def parse():
     ap.add_argument('--pool', type=int, default=8, help='distinct pre-built batches the timed steps rotate over')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--host-batcher', action='store_true', help='e2e with the all-host C++ batcher instead of the device batcher')
     return ap.parse_args()
 
 
@@ -226,6 +227,8 @@ def run_ours(args):
     R2 = 2 * tkg.num_r
 
     from renet_b200 import hoststore
+    if args.host_batcher:
+        hoststore.DEVICE_EDGES = False
     gstore = hoststore.GraphStore(tkg.graph_dict)
     hs_s = hoststore.HistoryStore(tkg.s_hist, tkg.s_hist_t, tkg.quads[:, 0], gstore)
     hs_o = hoststore.HistoryStore(tkg.o_hist, tkg.o_hist_t, tkg.quads[:, 2], gstore)
@@ -257,12 +260,19 @@ def run_ours(args):
         if ev is not None:
             ev[1].record()
 
+    step_no = [0]
+
     def device_step(e, events=None):
+        # every step is a new weight generation, as in training (the optimiser changes the weights between steps): the
+        # tcgen05 engine packs each self-loop matrix once per step and both directions use the image
+        step_no[0] += 1
+        L.renet_set_weight_generation(step_no[0])
         k = 0
         for d in e['dirs']:
             layer(d, ent, d['g'].node_ent, W1, L1, d['H1'], True, events[k] if events else None)
             layer(d, d['H1'], None, W2, L2, d['H2'], False, events[k + 1] if events else None)
             k += 2
+        L.renet_set_weight_generation(-1)
 
     def barrier():
         if world > 1:
@@ -356,18 +366,32 @@ def run_ours(args):
         for e in pool:
             e['q_pinned'] = torch.from_numpy(e['q']).pin_memory()
 
-        def run_e2e(n_steps, first):
-            entries = [pool[(first + i) % len(pool)] for i in range(n_steps)]
+        def run_e2e(n_warm, n_steps, first):
+            """ONE continuous stream of n_warm + n_steps steps through the loader; the clock starts when warm-up step
+            n_warm-1 has completed on the GPU, with the loader in steady state (it stays `depth` steps ahead of the
+            consumer at the start and at the end of the timed region alike), and stops when the last step's outputs are
+            on the host."""
+            entries = [pool[(first + i) % len(pool)] for i in range(n_warm + n_steps)]
             groups = ((e['vs'], e['vo']) for e in entries)
-            h2d = d2h = msgs = 0
+            h2d = d2h = 0
             prev = None
             checksum = 0.0
-            # host inputs -> C++ batcher in worker threads (steps i+1, i+2 are assembled while step i runs on the GPU);
+            graphs = []
+            t0 = None
+            # host inputs -> batch planning in worker threads (steps i+1, i+2 are prepared while step i runs on the GPU);
             # step i's result is read on the host (pinned D2H + event) right after step i+1 has been enqueued
-            for i, (e, hbs) in enumerate(zip(entries, hoststore.prefetch(groups, dev, depth=2, workers=4))):
+            for i, (e, hbs) in enumerate(zip(entries, hoststore.prefetch(groups, dev, depth=E2E_DEPTH, workers=E2E_WORKERS))):
+                if i == n_warm:
+                    if prev is not None:
+                        prev[0].synchronize()
+                        checksum += float(prev[1][0, 0])
+                        prev = None
+                    barrier()
+                    t0 = time.perf_counter()
                 a, b, ev = api_step(e, hbs, out_ring[i & 1])
-                h2d += a; d2h += b
-                msgs += sum(2 * hb.graph.E for hb in hbs)
+                if i >= n_warm:
+                    h2d += a; d2h += b
+                    graphs.extend(hb.graph for hb in hbs)      # edge counts come back asynchronously: summed after the loop
                 if prev is not None:
                     prev[0].synchronize()
                     checksum += float(prev[1][0, 0])
@@ -375,26 +399,28 @@ def run_ours(args):
             if prev is not None:
                 prev[0].synchronize()
                 checksum += float(prev[1][0, 0])
-            return h2d, d2h, msgs
+            barrier()
+            dt = time.perf_counter() - t0
+            msgs = sum(2 * g.E for g in graphs)
+            return h2d, d2h, msgs, dt
 
-        run_e2e(max(2, min(args.warmup, 3)), 0)
-        barrier()
-        k_e2e = max(4, min(args.steps, 12))
-        t0 = time.perf_counter()
-        h2d, d2h, msgs = run_e2e(k_e2e, args.warmup)
-        barrier()
-        dt = time.perf_counter() - t0
+        E2E_DEPTH, E2E_WORKERS = 4, 8
+        k_e2e = max(4, args.steps)
+        h2d, d2h, msgs, dt = run_e2e(max(3, args.warmup), k_e2e, 0)
         tt = torch.tensor([dt, float(msgs)], device=dev, dtype=torch.float64)
         if world > 1:
             a = tt.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
             b = tt.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
             dt, msgs = a[0].item(), b[1].item()
         e2e = {'value': msgs / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d / k_e2e), 'd2h_bytes_per_step': int(d2h / k_e2e),
-               'ms_per_step': dt / k_e2e * 1e3, 'steps': k_e2e,
-               'what': 'RENet.encode x2 directions from HOST inputs (flat history/graph stores + triplets): C++ batching '
-                       '(renet_host_assemble_batch, prefetched 2 steps ahead by worker threads) + one pinned H2D per '
-                       'direction + RGCN x2 + fused read-out/GRU + pinned D2H of the [B,2h] outputs every step (read one step '
-                       'behind the enqueue front)'}
+               'ms_per_step': dt / k_e2e * 1e3, 'steps': k_e2e, 'warmup': max(3, args.warmup),
+               'batcher': 'device (renet_host_plan_batch + renet_induce_edges)' if hoststore.DEVICE_EDGES else
+                          'host (renet_host_assemble_batch)',
+               'what': 'RENet.encode x2 directions from HOST inputs (flat history store + triplets; the per-timestamp graph '
+                       'store is resident in HBM like the parameters): host planning of the batch (sample order, components, '
+                       'node numbering, read-out rows; prepared %d steps ahead by %d worker threads)' % (E2E_DEPTH, E2E_WORKERS) + '  + one pinned H2D per '
+                       'direction + induced-edge CSR build on the GPU + RGCN x2 + fused read-out/GRU + pinned D2H of the '
+                       '[B,2h] outputs every step (read one step behind the enqueue front)'}
 
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
@@ -406,7 +432,7 @@ def run_ours(args):
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': WORKLOAD, 'step': '2 directions x 2 RGCN layers (tcgen05 3xTF32 self-loop GEMM + fused gather)',
+                'config': {'workload': WORKLOAD, 'step': '2 directions x 2 RGCN layers (tcgen05 3xTF32 self-loop GEMM + fused gather); every step is a new weight generation: each self-loop matrix is packed once per step and shared by both directions',
                            'nodes_per_direction': [d['g'].N for d in g0], 'edges_per_direction': [d['g'].E for d in g0],
                            'edge_msgs_per_step': msgs_per_step[0], 'l2': 'rotating-pool', 'pool_batches': len(pool),
                            'pool_bytes': int(pool_bytes), 'parallelism': 'dp%d (independent shards, no data-path collective)' % world},

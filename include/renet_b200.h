@@ -49,6 +49,13 @@ int renet_get_gemm_engine(void);
 /* Tuning knob for renet_rgcn_gather's d=200 kernel (tile size / occupancy variants, see rgcn_fwd.cu);
  * results are identical across variants.  Returns the previous value. */
 int renet_set_gather_variant(int variant);
+/* Packed-weight cache of the tcgen05 GEMM engine.  The engine consumes weights (self-loop matrices, GRU W_ih / W_hh)
+ * in a packed shared-memory operand image; packing is a kernel launch per weight per call.  Declaring a weight
+ * generation >= 0 promises that every weight passed by pointer is unchanged while the generation is unchanged: packed
+ * images are then kept per (device, pointers, shape) and reused, and any change of the generation invalidates all of
+ * them.  generation < 0 (default) disables the cache: weights are packed on every call.  The Python host derives the
+ * generation from the parameters' identities and in-place version counters. */
+int renet_set_weight_generation(int64_t generation);
 /* Optional caller-owned DEVICE scratch buffer (128-byte aligned) the tensor-core GEMM engine uses for the packed
  * (hi/lo split, K-major, 128-byte-swizzled) copy of the B operand, so that GEMM CTAs can fetch it with TMA bulk
  * copies.  Needs ceil(N/200)*ceil(K/32)*53248 bytes per GEMM (W_loop: 373 KB; GRU input projection: 2.2 MB); without
@@ -250,6 +257,39 @@ int renet_host_assemble_batch(
     const int64_t* sample_idx, int64_t B, int32_t sort, int32_t R2, int32_t n_hot_max,
     int64_t* s_idx_out, int32_t* out, int64_t out_capacity, int32_t* comp_graph_out,
     int32_t* batch_sizes_out, int32_t max_len_capacity, int64_t* sizes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device batcher: the same contract as renet_host_assemble_batch (reference utils.py:149-181,209-244), split so
+ * that only the O(S + nodes) part runs on the host and the O(edges) part -- utils.make_subgraph's induced-edge
+ * filter (utils.py:115-131) over every touched timestamp + dgl.batch (utils.py:238) -- runs on the GPU against a
+ * graph store resident in HBM.
+ *
+ * renet_host_plan_batch (host, no CUDA): orders the samples, picks the components, marks and numbers the nodes.
+ * `out` (int32 words, one H2D copy):
+ *   newid[M] node_ent[N] readout[S] row_comp[S] row_seq[S] seq_start[Q] seq_len[Q] packed_row[S] s_idx[B]
+ *   comp_graph[G] mark_off[G+1] cand_off[G+1]
+ * newid: per component c one word per local row of its graph (at mark_off[c]): batched node id, or -1;
+ * cand_off: prefix sum of the components' un-induced edge counts.  sizes [10] = {N, E_cand, S, Q, G, max_len,
+ * words_used, M, 0, 0}.  Returns 0, 1 when out_capacity < words_used (grow, call again), <0 on error.
+ *
+ * renet_induce_edges (device pointers only): filters the E_cand candidate edges and writes the batched graph's
+ * CSR by destination -- row_ptr [N+1], col_src / col_type_s / col_type_o (capacity E_cand, the first E entries
+ * are valid), norm [N] = 1/max(in-degree,1) (utils.py:126-127) -- and the edge count E into e_count[0].
+ * Identical, bit for bit, to renet_host_assemble_batch's output.
+ * ---------------------------------------------------------------------------------------------- */
+int renet_host_plan_batch(
+    int64_t T, const int64_t* g_node_off, const int32_t* g_node_ent, const int64_t* g_edge_off,
+    const int64_t* h_samp_off, const int64_t* h_samp_entry, const int32_t* h_ent_graph, const int32_t* h_ent_srow,
+    const int64_t* h_ent_off, const int32_t* h_nbr_row, const int64_t* sample_idx, int64_t B, int32_t sort,
+    int64_t* s_idx_out, int32_t* out, int64_t out_capacity, int32_t* batch_sizes_out, int32_t max_len_capacity,
+    int64_t* sizes);
+int64_t renet_induce_workspace_bytes(int64_t e_cand);
+int renet_induce_edges(const int64_t* g_edge_off, const int32_t* g_src, const int32_t* g_dst,
+                       const int32_t* g_type_s, const int32_t* g_type_o, const int32_t* comp_graph,
+                       const int32_t* mark_off, const int32_t* cand_off, const int32_t* newid, int64_t G,
+                       int64_t N, int64_t e_cand, int32_t* row_ptr, int32_t* col_src, int32_t* col_type_s,
+                       int32_t* col_type_o, float* norm, int32_t* e_count, void* workspace,
+                       int64_t workspace_bytes, void* stream);
 
 /* One call for the whole forward hot path of one direction (inference / no autograd):
  *   H1 = relu-layer(ent[node_ent]), H2 = linear-layer(H1)   (renet_rgcn_block_fwd x2, Aggregator.py:136-137)

@@ -21,6 +21,7 @@ SIGNATURES = {
     'renet_set_gemm_engine': (ctypes.c_int, [ctypes.c_int]),
     'renet_get_gemm_engine': (ctypes.c_int, []),
     'renet_set_gather_variant': (ctypes.c_int, [ctypes.c_int]),
+    'renet_set_weight_generation': (ctypes.c_int, [_i64]),
     'renet_set_scratch': (ctypes.c_int, [_vp, _i64]),
     'renet_csr_workspace_bytes': (_i64, [_i64, _i64]),
     'renet_build_csr': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
@@ -37,6 +38,9 @@ SIGNATURES = {
     'renet_gru_bwd': (ctypes.c_int, [_vp] * 11 + [_i32] + [_vp] * 18 + [_i64, _i64, _i64, _i64, _i32, _vp, _vp, _i64, _vp]),
     'renet_set_host_threads': (ctypes.c_int, [ctypes.c_int]),
     'renet_host_assemble_batch': (ctypes.c_int, [_i64] + [_vp] * 13 + [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
+    'renet_host_plan_batch': (ctypes.c_int, [_i64] + [_vp] * 10 + [_i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp]),
+    'renet_induce_workspace_bytes': (_i64, [_i64]),
+    'renet_induce_edges': (ctypes.c_int, [_vp] * 9 + [_i64, _i64, _i64] + [_vp] * 7 + [_i64, _vp]),
     'renet_encode_fwd': (ctypes.c_int, [_vp] * 12 + [_i64, _i64, _i32] + [_vp] * 9 + [_i32] + [_vp] * 10 +
                          [_i64, _i64, _i64, _i32, _i32, _vp, _i64, _vp]),
     'renet_pack_inputs': (ctypes.c_int, [_vp] * 12 + [_i64, _i32, _vp]),
@@ -102,3 +106,29 @@ def ensure_scratch(device, nbytes=16 << 20):
 
 def launch_count():
     return int(lib().renet_launch_count())
+
+
+# ---- packed-weight cache (renet_set_weight_generation) -----------------------------------------------------------------
+_pack_tokens = __import__('itertools').count(1)
+
+
+def new_pack_token():
+    """Unique id of a module instance: part of its weight generation, so that another module whose parameters happen to
+    be allocated at the same addresses can never hit this one's packed images."""
+    return next(_pack_tokens)
+
+
+class weight_generation:
+    """Context manager: while active, the tcgen05 GEMM engine may reuse packed weight images made under the same
+    generation = hash(module token, (address, in-place version) of every weight).  Outside of it the cache is off, so
+    direct C-ABI callers are never served a stale image."""
+
+    def __init__(self, token, params):
+        self.gen = hash((token,) + tuple((p.data_ptr(), p._version) for p in params)) & ((1 << 62) - 1)
+
+    def __enter__(self):
+        lib().renet_set_weight_generation(self.gen)
+
+    def __exit__(self, *exc):
+        lib().renet_set_weight_generation(-1)
+        return False

@@ -65,6 +65,7 @@ class RGCNAggregator(nn.Module):
                                activation=F.relu, self_loop=True, dropout=dropout)
         self.rgcn2 = RGCNLayer(self.h_dim, self.h_dim, 2 * self.num_rels, num_bases,
                                activation=None, self_loop=True, dropout=dropout)
+        self._pack_token = _lib.new_pack_token()
 
     # ---------------------------------------------------------------------------------------------
     def _batch(self, s_hist, s, graph_dict, device, sort):
@@ -136,13 +137,18 @@ class RGCNAggregator(nn.Module):
         from .gru import fused_gru
         dev = ent_embeds.device
         hb = self._batch(hist, s, graph_dict, dev, True)
-        if not torch.is_grad_enabled() and not self.training:
-            return self._encode_inference(hb, s, r, ent_embeds, rel_embeds, global_emb, reverse, encoder, encoder_r)
-        H2 = self.aggregate(hb, ent_embeds, reverse)
-        glob = global_rows_of_batch(global_emb, hb, self.h_dim, dev)
-        _, _, seq_s, seq_r = self._sorted_ids(hb, s, r, dev)
-        s_h, s_q = fused_gru(H2, ent_embeds, rel_embeds, glob, hb, seq_s, seq_r, encoder, encoder_r)
-        return s_h, s_q, hb
+        # weights the tcgen05 GEMM engine packs: unchanged weights (same addresses, same in-place versions) are packed
+        # once and reused across calls -- both directions of a step, and every step in inference
+        weights = [self.rgcn1.loop_weight, self.rgcn2.loop_weight, encoder.weight_ih_l0, encoder.weight_hh_l0,
+                   encoder_r.weight_ih_l0, encoder_r.weight_hh_l0]
+        with _lib.weight_generation(self._pack_token, weights):
+            if not torch.is_grad_enabled() and not self.training:
+                return self._encode_inference(hb, s, r, ent_embeds, rel_embeds, global_emb, reverse, encoder, encoder_r)
+            H2 = self.aggregate(hb, ent_embeds, reverse)
+            glob = global_rows_of_batch(global_emb, hb, self.h_dim, dev)
+            _, _, seq_s, seq_r = self._sorted_ids(hb, s, r, dev)
+            s_h, s_q = fused_gru(H2, ent_embeds, rel_embeds, glob, hb, seq_s, seq_r, encoder, encoder_r)
+            return s_h, s_q, hb
 
     def _encode_inference(self, hb, s, r, ent_embeds, rel_embeds, global_emb, reverse, encoder, encoder_r):
         """No-autograd fast path: the whole direction (2 RGCN layers + read-out + both GRUs) is ONE C-ABI call
@@ -168,7 +174,7 @@ class RGCNAggregator(nn.Module):
         l1, l2 = self.rgcn1, self.rgcn2
         rc = L.renet_encode_fwd(P(ent_embeds), P(g.node_ent), P(g.row_ptr), P(g.col_src), P(g.col_type(reverse)),
                                 P(g.norm), P(l1.weight), P(l1.loop_weight), P(l2.weight), P(l2.loop_weight), P(H[0]),
-                                P(H[1]), g.N, g.E, l1.weight.shape[0], P(hb.readout), P(hb.row_glob), P(glob), P(rel),
+                                P(H[1]), g.N, g.E_launch, l1.weight.shape[0], P(hb.readout), P(hb.row_glob), P(glob), P(rel),
                                 P(seq_s), P(seq_r), P(g.seq_len_dev), P(hb.seq_start),
                                 bs.ctypes.data_as(_lib.ctypes.c_void_p), len(bs), P(p4[0]), P(p4[1]), P(p4[2]), P(p4[3]),
                                 P(p3[0]), P(p3[1]), P(p3[2]), P(p3[3]), P(hn[0]), P(hn[1]), hb.S, Q, T, h, l1.num_bases,

@@ -110,6 +110,7 @@ int64_t renet_launch_count(void) { return g_launches.load(); }
 int renet_set_gemm_engine(int engine) { return set_gemm_mode(engine); }
 int renet_get_gemm_engine(void) { return gemm_mode(); }
 int renet_set_gather_variant(int variant) { return set_gather_variant(variant); }
+int renet_set_weight_generation(int64_t generation) { renet::set_weight_generation(generation); return RENET_OK; }
 int renet_set_scratch(void* device_ptr, int64_t bytes) {
   RENET_CHECK_ARG(bytes >= 0 && (device_ptr != nullptr || bytes == 0), "renet_set_scratch: bad arguments");
   set_scratch(device_ptr, bytes);

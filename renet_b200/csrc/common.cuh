@@ -77,6 +77,10 @@ int sgemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
 // tcgen05 GEMM engine building blocks (umma_gemm.cu); gemm_mode() == 1 selects the engine
 int gemm_mode();
 int64_t umma_packed_bytes(int N, int K);
+// packed-weight cache (umma_gemm.cu): persistent device buffer for this key, or nullptr when caching is off; *hit says
+// whether it already holds the image for the current weight generation
+void set_weight_generation(int64_t g);
+void* packed_cache_lookup(const void* const* keys, int nkeys, int64_t bytes, bool* hit);
 bool umma_shape_ok(int N, int K);
 int umma_pack_b(const float* B, int64_t sk, int64_t sn, int N, int K, void* Bp, int tile_offset, cudaStream_t stream);
 int umma_gemm_prepacked(const float* A, const int32_t* a_index, int64_t lda, const void* Bp, float* C, int64_t ldc,

@@ -189,16 +189,30 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
                         (reinterpret_cast<uintptr_t>(ws_base) & 127) == 0;
   if (use_umma) {
     const int t3 = 3 * h / 200;   // column tiles per encoder
-    // logical B[k][n] = w[n][col_off + k]  ->  sk = 1, sn = leading dimension of w
-    if ((rc = umma_pack_b(w_ih4, 1, 4 * h, 3 * h, h, w.P_row, 0, stream))) return rc;
-    if ((rc = umma_pack_b(w_ih3, 1, 3 * h, 3 * h, h, w.P_row, t3, stream))) return rc;
-    if ((rc = umma_pack_b(w_ih4 + h, 1, 4 * h, 3 * h, h, w.P_ent, 0, stream))) return rc;
-    if ((rc = umma_pack_b(w_ih3 + h, 1, 3 * h, 3 * h, h, w.P_ent, t3, stream))) return rc;
-    if ((rc = umma_pack_b(w_ih4 + 2 * h, 1, 4 * h, 3 * h, h, w.P_rel, 0, stream))) return rc;
-    if ((rc = umma_pack_b(w_ih4 + 3 * h, 1, 4 * h, 3 * h, h, w.P_glob, 0, stream))) return rc;
-    if ((rc = umma_pack_b(w_ih3 + 2 * h, 1, 3 * h, 3 * h, h, w.P_glob, t3, stream))) return rc;
-    if ((rc = umma_pack_b(w_hh4, 1, h, 3 * h, h, w.P_hh, 0, stream))) return rc;
-    if ((rc = umma_pack_b(w_hh3, 1, h, 3 * h, h, reinterpret_cast<uint8_t*>(w.P_hh) + w.p_hh_bytes, 0, stream))) return rc;
+    // the packed images only change with the weights: with a declared weight generation they are cached across calls
+    {
+      const void* keys[5] = {w_ih4, w_ih3, w_hh4, w_hh3, reinterpret_cast<const void*>((intptr_t)h)};
+      const int64_t p_bytes = ((w.P_hh - w.P_row) * 4) + 2 * w.p_hh_bytes;
+      bool hit = false;
+      float* cached = static_cast<float*>(packed_cache_lookup(keys, 5, p_bytes, &hit));
+      if (cached) {
+        const float* base = w.P_row;
+        w.P_ent = cached + (w.P_ent - base); w.P_rel = cached + (w.P_rel - base); w.P_glob = cached + (w.P_glob - base);
+        w.P_hh = cached + (w.P_hh - base); w.P_row = cached;
+      }
+      if (!hit) {
+        // logical B[k][n] = w[n][col_off + k]  ->  sk = 1, sn = leading dimension of w
+        if ((rc = umma_pack_b(w_ih4, 1, 4 * h, 3 * h, h, w.P_row, 0, stream))) return rc;
+        if ((rc = umma_pack_b(w_ih3, 1, 3 * h, 3 * h, h, w.P_row, t3, stream))) return rc;
+        if ((rc = umma_pack_b(w_ih4 + h, 1, 4 * h, 3 * h, h, w.P_ent, 0, stream))) return rc;
+        if ((rc = umma_pack_b(w_ih3 + h, 1, 3 * h, 3 * h, h, w.P_ent, t3, stream))) return rc;
+        if ((rc = umma_pack_b(w_ih4 + 2 * h, 1, 4 * h, 3 * h, h, w.P_rel, 0, stream))) return rc;
+        if ((rc = umma_pack_b(w_ih4 + 3 * h, 1, 4 * h, 3 * h, h, w.P_glob, 0, stream))) return rc;
+        if ((rc = umma_pack_b(w_ih3 + 2 * h, 1, 3 * h, 3 * h, h, w.P_glob, t3, stream))) return rc;
+        if ((rc = umma_pack_b(w_hh4, 1, h, 3 * h, h, w.P_hh, 0, stream))) return rc;
+        if ((rc = umma_pack_b(w_hh3, 1, h, 3 * h, h, reinterpret_cast<uint8_t*>(w.P_hh) + w.p_hh_bytes, 0, stream))) return rc;
+      }
+    }
     concat_bias_kernel<<<(6 * h + 255) / 256, 256, 0, stream>>>(b_ih4, b_ih3, w.bih, 3 * h);
     RENET_CHECK_LAUNCH("concat_bias_kernel");
     concat_bias_kernel<<<(6 * h + 255) / 256, 256, 0, stream>>>(b_hh4, b_hh3, w.bhh, 3 * h);

@@ -47,6 +47,109 @@ extern "C" int renet_set_host_threads(int n) {
   return prev;
 }
 
+namespace {
+// Steps 1-3 of the batching, shared by the all-host batcher and the host half of the device batcher.
+struct Plan {
+  std::vector<int32_t> len, comp_graph, row_comp, row_srow, row_seq, newid;
+  std::vector<int64_t> mark_off, comp_start;
+  int max_len = 0;
+  int64_t Q = 0, S = 0, G = 0, N = 0;
+};
+
+// returns RENET_OK / error; S == 0 leaves the plan empty
+int build_plan(Plan& P, const char* fn, int64_t T, const int64_t* g_node_off, const int64_t* h_samp_off,
+               const int64_t* h_samp_entry, const int32_t* h_ent_graph, const int32_t* h_ent_srow, const int64_t* h_ent_off,
+               const int32_t* h_nbr_row, const int64_t* sample_idx, int64_t B, int32_t sort, int64_t* s_idx_out,
+               int32_t max_len_capacity) {
+  // ---- 1. order samples by history length, descending, stable (model.py:80-81, utils.py:212-215) ----
+  P.len.resize(B);
+  int max_len = 0;
+  for (int64_t i = 0; i < B; ++i) {
+    P.len[i] = (int32_t)(h_samp_off[sample_idx[i] + 1] - h_samp_off[sample_idx[i]]);
+    max_len = std::max(max_len, (int)P.len[i]);
+  }
+  if (max_len > max_len_capacity) { renet::set_error("%s: history longer than %d", fn, max_len_capacity); return RENET_ERR_INVALID_ARG; }
+  P.max_len = max_len;
+  int64_t Q = 0, S = 0;
+  if (sort) {
+    std::vector<int64_t> start(max_len + 2, 0);
+    for (int64_t i = 0; i < B; ++i) start[max_len - P.len[i] + 1]++;       // bucket by (max_len - len)
+    for (int k = 0; k <= max_len; ++k) start[k + 1] += start[k];
+    for (int64_t i = 0; i < B; ++i) s_idx_out[start[max_len - P.len[i]]++] = i;
+  } else {
+    for (int64_t i = 0; i < B; ++i) s_idx_out[i] = i;
+  }
+  for (int64_t i = 0; i < B; ++i) if (P.len[i] > 0) { ++Q; S += P.len[i]; }
+  if (!sort) {   // unsorted twin (utils.py:251-255) takes the FIRST Q samples: they must be the non-empty ones
+    for (int64_t i = 0; i < Q; ++i)
+      if (P.len[i] == 0) { renet::set_error("%s: unsorted batches must list their non-empty histories first", fn); return RENET_ERR_INVALID_ARG; }
+  }
+  P.Q = Q; P.S = S;
+  if (S == 0) return RENET_OK;
+  // ---- 2. components = distinct timestamps in first-appearance order (utils.py:149-170) ----------------
+  std::vector<int32_t> comp_of_graph(T, -1);
+  P.row_comp.resize(S); P.row_srow.resize(S); P.row_seq.resize(S);
+  std::vector<int64_t> row_entry(S);
+  int64_t r = 0;
+  for (int64_t q = 0; q < Q; ++q) {
+    const int64_t smp = sample_idx[s_idx_out[q]];
+    for (int64_t ei = h_samp_off[smp]; ei < h_samp_off[smp + 1]; ++ei, ++r) {
+      const int64_t e = h_samp_entry[ei];
+      const int32_t g = h_ent_graph[e];
+      if (comp_of_graph[g] < 0) { comp_of_graph[g] = (int32_t)P.comp_graph.size(); P.comp_graph.push_back(g); }
+      P.row_comp[r] = comp_of_graph[g];
+      P.row_srow[r] = h_ent_srow[e];
+      P.row_seq[r] = (int32_t)q;
+      row_entry[r] = e;
+    }
+  }
+  const int64_t G = P.G = (int64_t)P.comp_graph.size();
+  // ---- 3. node sets: mark local rows of every component's graph, then number them ----------------------------
+  P.mark_off.assign(G + 1, 0);
+  for (int64_t c = 0; c < G; ++c) P.mark_off[c + 1] = P.mark_off[c] + (g_node_off[P.comp_graph[c] + 1] - g_node_off[P.comp_graph[c]]);
+  P.newid.assign(P.mark_off[G], -1);       // -1 = not selected; later the batched node id
+  for (int64_t i = 0; i < S; ++i) {
+    int32_t* m = P.newid.data() + P.mark_off[P.row_comp[i]];
+    m[P.row_srow[i]] = 0;
+    const int64_t e = row_entry[i];
+    for (int64_t k = h_ent_off[e]; k < h_ent_off[e + 1]; ++k) m[h_nbr_row[k]] = 0;
+  }
+  int64_t N = 0;
+  P.comp_start.assign(G + 1, 0);
+  for (int64_t c = 0; c < G; ++c) {
+    P.comp_start[c] = N;
+    int32_t* m = P.newid.data() + P.mark_off[c];
+    const int64_t n = P.mark_off[c + 1] - P.mark_off[c];
+    for (int64_t j = 0; j < n; ++j) if (m[j] == 0) m[j] = (int32_t)N++;
+  }
+  P.comp_start[G] = N;
+  P.N = N;
+  return RENET_OK;
+}
+
+// read-out rows + sequence bookkeeping (utils.py:172-181, Aggregator.py:160-165)
+void emit_sequences(const Plan& P, const int64_t* s_idx_out, int32_t* o_readout, int32_t* o_rowcomp, int32_t* o_rowseq,
+                    int32_t* o_seqstart, int32_t* o_seqlen, int32_t* o_packed, int32_t* batch_sizes_out) {
+  for (int64_t i = 0; i < P.S; ++i) {
+    o_readout[i] = P.newid[P.mark_off[P.row_comp[i]] + P.row_srow[i]];
+    o_rowcomp[i] = P.row_comp[i];
+    o_rowseq[i] = P.row_seq[i];
+  }
+  int64_t acc = 0;
+  for (int64_t q = 0; q < P.Q; ++q) {
+    o_seqstart[q] = (int32_t)acc;
+    o_seqlen[q] = P.len[s_idx_out[q]];
+    acc += o_seqlen[q];
+  }
+  int64_t p = 0;
+  for (int t = 0; t < P.max_len; ++t) {
+    int32_t n_act = 0;
+    for (int64_t q = 0; q < P.Q; ++q) if (o_seqlen[q] > t) { o_packed[p++] = o_seqstart[q] + t; ++n_act; }
+    batch_sizes_out[t] = n_act;
+  }
+}
+}  // namespace
+
 extern "C" int renet_host_assemble_batch(
     // ---- graph store ------------------------------------------------------------------------------
     int64_t T, const int64_t* g_node_off, const int32_t* g_node_ent, const int64_t* g_edge_off,
@@ -61,69 +164,18 @@ extern "C" int renet_host_assemble_batch(
     int32_t max_len_capacity,
     int64_t* sizes /* [10]: N, E, S, Q, G, max_len, words_used, n_hot_s, n_hot_o, 0 */) {
   if (B < 0 || !sizes || R2 < 0 || n_hot_max < 0) { renet::set_error("renet_host_assemble_batch: bad arguments"); return RENET_ERR_INVALID_ARG; }
-  // ---- 1. order samples by history length, descending, stable (model.py:80-81, utils.py:212-215) ----
-  std::vector<int32_t> len(B);
-  int max_len = 0;
-  for (int64_t i = 0; i < B; ++i) {
-    len[i] = (int32_t)(h_samp_off[sample_idx[i] + 1] - h_samp_off[sample_idx[i]]);
-    max_len = std::max(max_len, (int)len[i]);
-  }
-  if (max_len > max_len_capacity) { renet::set_error("renet_host_assemble_batch: history longer than %d", max_len_capacity); return RENET_ERR_INVALID_ARG; }
-  int64_t Q = 0, S = 0;
-  if (sort) {
-    std::vector<int64_t> start(max_len + 2, 0);
-    for (int64_t i = 0; i < B; ++i) start[max_len - len[i] + 1]++;       // bucket by (max_len - len)
-    for (int k = 0; k <= max_len; ++k) start[k + 1] += start[k];
-    for (int64_t i = 0; i < B; ++i) s_idx_out[start[max_len - len[i]]++] = i;
-  } else {
-    for (int64_t i = 0; i < B; ++i) s_idx_out[i] = i;
-  }
-  for (int64_t i = 0; i < B; ++i) if (len[i] > 0) { ++Q; S += len[i]; }
-  if (!sort) {   // unsorted twin (utils.py:251-255) takes the FIRST Q samples: they must be the non-empty ones
-    for (int64_t i = 0; i < Q; ++i)
-      if (len[i] == 0) { renet::set_error("renet_host_assemble_batch: unsorted batches must list their non-empty histories first"); return RENET_ERR_INVALID_ARG; }
-  }
+  Plan P;
+  int prc = build_plan(P, "renet_host_assemble_batch", T, g_node_off, h_samp_off, h_samp_entry, h_ent_graph, h_ent_srow,
+                       h_ent_off, h_nbr_row, sample_idx, B, sort, s_idx_out, max_len_capacity);
+  if (prc != RENET_OK) return prc;
+  const int64_t Q = P.Q, S = P.S, G = P.G, N = P.N;
+  const int max_len = P.max_len;
   sizes[2] = S; sizes[3] = Q; sizes[5] = max_len;
   if (S == 0) { sizes[0] = sizes[1] = sizes[4] = sizes[6] = 0; return RENET_OK; }
-
-  // ---- 2. components = distinct timestamps in first-appearance order (utils.py:149-170) ----------------
-  std::vector<int32_t> comp_of_graph(T, -1);
-  std::vector<int32_t> comp_graph;
-  std::vector<int32_t> row_comp(S), row_srow(S), row_seq(S);
-  std::vector<int64_t> row_entry(S);
-  int64_t r = 0;
-  for (int64_t q = 0; q < Q; ++q) {
-    const int64_t smp = sample_idx[s_idx_out[q]];
-    for (int64_t ei = h_samp_off[smp]; ei < h_samp_off[smp + 1]; ++ei, ++r) {
-      const int64_t e = h_samp_entry[ei];
-      const int32_t g = h_ent_graph[e];
-      if (comp_of_graph[g] < 0) { comp_of_graph[g] = (int32_t)comp_graph.size(); comp_graph.push_back(g); }
-      row_comp[r] = comp_of_graph[g];
-      row_srow[r] = h_ent_srow[e];
-      row_seq[r] = (int32_t)q;
-      row_entry[r] = e;
-    }
-  }
-  const int64_t G = (int64_t)comp_graph.size();
-  // ---- 3. node sets: mark local rows of every component's graph -------------------------------------------
-  std::vector<int64_t> mark_off(G + 1, 0);
-  for (int64_t c = 0; c < G; ++c) mark_off[c + 1] = mark_off[c] + (g_node_off[comp_graph[c] + 1] - g_node_off[comp_graph[c]]);
-  std::vector<int32_t> newid(mark_off[G], -1);       // -1 = not selected; later the batched node id
-  for (int64_t i = 0; i < S; ++i) {
-    int32_t* m = newid.data() + mark_off[row_comp[i]];
-    m[row_srow[i]] = 0;
-    const int64_t e = row_entry[i];
-    for (int64_t k = h_ent_off[e]; k < h_ent_off[e + 1]; ++k) m[h_nbr_row[k]] = 0;
-  }
-  int64_t N = 0;
-  std::vector<int64_t> comp_start(G + 1, 0);
-  for (int64_t c = 0; c < G; ++c) {
-    comp_start[c] = N;
-    int32_t* m = newid.data() + mark_off[c];
-    const int64_t n = mark_off[c + 1] - mark_off[c];
-    for (int64_t j = 0; j < n; ++j) if (m[j] == 0) m[j] = (int32_t)N++;
-  }
-  comp_start[G] = N;
+  const std::vector<int32_t>& comp_graph = P.comp_graph;
+  const std::vector<int32_t>& newid = P.newid;
+  const std::vector<int64_t>& mark_off = P.mark_off;
+  const std::vector<int64_t>& comp_start = P.comp_start;
   // ---- 4. count induced edges per component (utils.make_subgraph, utils.py:115-131), in parallel -------------
   std::vector<int64_t> comp_estart(G + 1, 0);
   parallel_for(G, [&](int64_t c) {
@@ -178,24 +230,8 @@ extern "C" int renet_host_assemble_batch(
     const int32_t d = o_rp[v + 1] - o_rp[v];
     o_norm[v] = 1.0f / (float)(d > 0 ? d : 1);       // recomputed per sub-graph (utils.py:126-127)
   }
-  // ---- 6. read-out rows + sequence bookkeeping (utils.py:172-181, Aggregator.py:160-165) -------------------------
-  for (int64_t i = 0; i < S; ++i) {
-    o_readout[i] = newid[mark_off[row_comp[i]] + row_srow[i]];
-    o_rowcomp[i] = row_comp[i];
-    o_rowseq[i] = row_seq[i];
-  }
-  int64_t acc = 0;
-  for (int64_t q = 0; q < Q; ++q) {
-    o_seqstart[q] = (int32_t)acc;
-    o_seqlen[q] = len[s_idx_out[q]];
-    acc += o_seqlen[q];
-  }
-  int64_t p = 0;
-  for (int t = 0; t < max_len; ++t) {
-    int32_t n_act = 0;
-    for (int64_t q = 0; q < Q; ++q) if (o_seqlen[q] > t) { o_packed[p++] = o_seqstart[q] + t; ++n_act; }
-    batch_sizes_out[t] = n_act;
-  }
+  // ---- 6. read-out rows + sequence bookkeeping ------------------------------------------------------------------
+  emit_sequences(P, s_idx_out, o_readout, o_rowcomp, o_rowseq, o_seqstart, o_seqlen, o_packed, batch_sizes_out);
   for (int64_t c = 0; c < G; ++c) comp_graph_out[c] = comp_graph[c];
   // ---- 7. component table (largest first) and the hottest relations of this batch, for renet_rgcn_gather_comp ----
   int32_t* o_cptr = o_packed + S;
@@ -229,5 +265,69 @@ extern "C" int renet_host_assemble_batch(
   for (int64_t i = 0; i < B; ++i) o_sidx[i] = (int32_t)s_idx_out[i];
   int32_t* o_cg = o_sidx + B;
   for (int64_t c = 0; c < G; ++c) o_cg[c] = comp_graph[c];
+  return RENET_OK;
+}
+
+// Host half of the DEVICE batcher: steps 1-3 + 6 only (everything whose cost is O(S + nodes)); the O(edges) part --
+// filtering every candidate edge of the touched timestamps against the node marks and emitting the CSR -- is
+// renet_induce_edges (device_batch.cu) on the GPU against a graph store resident in HBM.
+//
+// layout of `out` (int32 words):
+//   newid[M] node_ent[N] readout[S] row_comp[S] row_seq[S] seq_start[Q] seq_len[Q] packed_row[S] s_idx[B] comp_graph[G]
+//   mark_off[G+1] cand_off[G+1]
+// newid: per component c, one word per local row of its timestamp's graph (offset mark_off[c]): batched node id or -1;
+// cand_off: prefix sum of the components' (un-induced) edge counts, i.e. the candidate edges the device filters.
+extern "C" int renet_host_plan_batch(
+    int64_t T, const int64_t* g_node_off, const int32_t* g_node_ent, const int64_t* g_edge_off,
+    const int64_t* h_samp_off, const int64_t* h_samp_entry, const int32_t* h_ent_graph, const int32_t* h_ent_srow,
+    const int64_t* h_ent_off, const int32_t* h_nbr_row, const int64_t* sample_idx, int64_t B, int32_t sort,
+    int64_t* s_idx_out, int32_t* out, int64_t out_capacity, int32_t* batch_sizes_out, int32_t max_len_capacity,
+    int64_t* sizes /* [10]: N, E_cand, S, Q, G, max_len, words_used, M, 0, 0 */) {
+  if (B < 0 || !sizes) { renet::set_error("renet_host_plan_batch: bad arguments"); return RENET_ERR_INVALID_ARG; }
+  Plan P;
+  int prc = build_plan(P, "renet_host_plan_batch", T, g_node_off, h_samp_off, h_samp_entry, h_ent_graph, h_ent_srow, h_ent_off,
+                       h_nbr_row, sample_idx, B, sort, s_idx_out, max_len_capacity);
+  if (prc != RENET_OK) return prc;
+  const int64_t Q = P.Q, S = P.S, G = P.G, N = P.N;
+  for (int i = 0; i < 10; ++i) sizes[i] = 0;
+  sizes[2] = S; sizes[3] = Q; sizes[5] = P.max_len;
+  if (S == 0) return RENET_OK;
+  const int64_t M = P.mark_off[G];
+  int64_t e_cand = 0;
+  for (int64_t c = 0; c < G; ++c) e_cand += g_edge_off[P.comp_graph[c] + 1] - g_edge_off[P.comp_graph[c]];
+  if (M >= (int64_t(1) << 31) || e_cand >= (int64_t(1) << 31)) { renet::set_error("renet_host_plan_batch: batch too large for 32-bit offsets"); return RENET_ERR_INVALID_ARG; }
+  const int64_t words = M + N + 3 * S + 2 * Q + S + B + G + 2 * (G + 1);
+  sizes[0] = N; sizes[1] = e_cand; sizes[4] = G; sizes[6] = words; sizes[7] = M;
+  if (words > out_capacity) return 1;   // caller grows the staging buffer and retries
+  int32_t* o_newid = out;
+  int32_t* o_node = o_newid + M;
+  int32_t* o_readout = o_node + N;
+  int32_t* o_rowcomp = o_readout + S;
+  int32_t* o_rowseq = o_rowcomp + S;
+  int32_t* o_seqstart = o_rowseq + S;
+  int32_t* o_seqlen = o_seqstart + Q;
+  int32_t* o_packed = o_seqlen + Q;
+  int32_t* o_sidx = o_packed + S;
+  int32_t* o_cg = o_sidx + B;
+  int32_t* o_moff = o_cg + G;
+  int32_t* o_coff = o_moff + G + 1;
+  memcpy(o_newid, P.newid.data(), (size_t)M * 4);
+  for (int64_t c = 0; c < G; ++c) {
+    const int32_t* m = P.newid.data() + P.mark_off[c];
+    const int32_t* ent = g_node_ent + g_node_off[P.comp_graph[c]];
+    const int64_t n = P.mark_off[c + 1] - P.mark_off[c];
+    for (int64_t j = 0; j < n; ++j) if (m[j] >= 0) o_node[m[j]] = ent[j];
+  }
+  emit_sequences(P, s_idx_out, o_readout, o_rowcomp, o_rowseq, o_seqstart, o_seqlen, o_packed, batch_sizes_out);
+  for (int64_t i = 0; i < B; ++i) o_sidx[i] = (int32_t)s_idx_out[i];
+  int64_t acc = 0;
+  for (int64_t c = 0; c < G; ++c) {
+    o_cg[c] = P.comp_graph[c];
+    o_moff[c] = (int32_t)P.mark_off[c];
+    o_coff[c] = (int32_t)acc;
+    acc += g_edge_off[P.comp_graph[c] + 1] - g_edge_off[P.comp_graph[c]];
+  }
+  o_moff[G] = (int32_t)M;
+  o_coff[G] = (int32_t)acc;
   return RENET_OK;
 }

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "rgcn_tile.cuh"
 #include "rgcn_comp.cuh"
+#include "rgcn_ring.cuh"
 
 namespace renet {
 namespace {
@@ -26,14 +27,19 @@ __global__ void __launch_bounds__(kTileWarps * 32, 3)
 rgcn_gather_d200_kernel(const float* __restrict__ H, const int32_t* __restrict__ h_index,
                         const float* __restrict__ W, const int32_t* __restrict__ row_ptr,
                         const int32_t* __restrict__ col_src, const int32_t* __restrict__ col_type,
-                        const float* __restrict__ norm, float* __restrict__ Hout, int N, int passthrough) {
+                        const float* __restrict__ norm, float* __restrict__ Hout, int N, int passthrough,
+                        const int32_t* __restrict__ tile_order) {
   __shared__ __align__(16) float agg[NODES][200];
   __shared__ __align__(16) float loopbuf[HAS_LOOP ? NODES : 1][200];
+  constexpr bool DET = (VARIANT == 0);     // deterministic, atomic-free hand-over of partial sums (rgcn_tile.cuh)
+  __shared__ __align__(16) float head[DET ? kTileWarps : 1][200];
+  __shared__ int head_mask[NODES];
   __shared__ float normbuf[NODES];
   __shared__ int s_rp[NODES + 1];
   const int tid = threadIdx.x;
   const int n_tiles = (N + NODES - 1) / NODES;
-  int tile_lo = blockIdx.x, tile_hi = blockIdx.x + 1;
+  // tile_order (optional): heaviest tiles first, so the last wave of CTAs is the lightest (LPT scheduling)
+  int tile_lo = tile_order ? __ldg(tile_order + blockIdx.x) : blockIdx.x, tile_hi = tile_lo + 1;
   if (VARIANT == 2) {
     const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
     tile_lo = blockIdx.x * per;
@@ -44,17 +50,22 @@ rgcn_gather_d200_kernel(const float* __restrict__ H, const int32_t* __restrict__
   const int v0 = tile * NODES;
   const int nv = min(NODES, N - v0);
   tile_prefetch_epilogue(loopbuf, normbuf, Hout + (int64_t)v0 * 200, norm + v0, nv, HAS_LOOP, tid, kTileWarps * 32);
-  for (int i = tid; i < NODES * 200; i += kTileWarps * 32) (&agg[0][0])[i] = 0.f;
+  if (DET) {
+    if (tid < NODES) head_mask[tid] = 0;
+  } else {
+    for (int i = tid; i < NODES * 200; i += kTileWarps * 32) (&agg[0][0])[i] = 0.f;
+  }
   if (tid <= nv) s_rp[tid] = __ldg(row_ptr + v0 + tid);
   __syncthreads();
-  tile_accumulate<false, INDEXED, false, VARIANT == 0>(agg, s_rp, nv, H, h_index, W, col_src, col_type, nullptr);
+  const TileHeads th{head, head_mask};
+  tile_accumulate<false, INDEXED, false, VARIANT == 0, DET>(agg, s_rp, nv, H, h_index, W, col_src, col_type, nullptr, th);
   cp_async_wait_all();
   __syncthreads();
   // epilogue: nv rows x 100 float2, coalesced; self-loop rows and norms were prefetched into shared memory
   for (int i = tid; i < nv * 100; i += kTileWarps * 32) {
     const int r = i / 100, c = (i % 100) * 2;
     const int v = v0 + r;
-    float2 a = *reinterpret_cast<const float2*>(&agg[r][c]);
+    float2 a = DET ? tile_row_sum(agg, th, s_rp, r, c) : *reinterpret_cast<const float2*>(&agg[r][c]);
     if (passthrough) {  // graph without edges: DGL 0.4 skips the reduce, h is left as is
       const int64_t hr = INDEXED ? (int64_t)__ldg(h_index + v) : v;
       a = *reinterpret_cast<const float2*>(H + hr * 200 + c);
@@ -308,19 +319,22 @@ int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, c
     const int variant = passthrough ? 0 : gather_variant();
     const unsigned n_tiles = (unsigned)((N + kTileNodes - 1) / kTileNodes);
     const unsigned grid = variant == 2 ? min(n_tiles, (unsigned)(kNumSMs * 3)) : n_tiles;
+    const int32_t* order = nullptr;   // optional heaviest-first tile order: measured, no gain
 #define RENET_LAUNCH_GATHER(R, L, I)                                                                            \
-  if (variant == 3)                                                                                             \
+  if (variant == 6)                                                                                             \
+    rgcn_gather_ring_kernel<R, L, I><<<n_tiles, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N); \
+  else if (variant == 3)                                                                                             \
     rgcn_gather_half_kernel<R, L, I, 4, 4><<<dim3(n_tiles, 2), block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N); \
   else if (variant == 4)                                                                                        \
     rgcn_gather_half_kernel<R, L, I, 2, 6><<<dim3(n_tiles, 2), block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N); \
   else if (variant == 5)                                                                                        \
     rgcn_gather_half_kernel<R, L, I, 3, 5><<<dim3(n_tiles, 2), block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N); \
   else if (variant == 1)                                                                                        \
-    rgcn_gather_d200_kernel<R, L, I, kTileNodes, 1><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough); \
+    rgcn_gather_d200_kernel<R, L, I, kTileNodes, 1><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough, nullptr); \
   else if (variant == 2)                                                                                        \
-    rgcn_gather_d200_kernel<R, L, I, kTileNodes, 2><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough); \
+    rgcn_gather_d200_kernel<R, L, I, kTileNodes, 2><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough, nullptr); \
   else                                                                                                          \
-    rgcn_gather_d200_kernel<R, L, I, kTileNodes, 0><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough)
+    rgcn_gather_d200_kernel<R, L, I, kTileNodes, 0><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough, order)
     const int key = (relu ? 4 : 0) | (has_loop ? 2 : 0) | (h_index ? 1 : 0);
     switch (key) {
       case 0: RENET_LAUNCH_GATHER(false, false, false); break;

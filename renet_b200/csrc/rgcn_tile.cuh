@@ -81,15 +81,47 @@ __device__ __forceinline__ void fma_edge(float (&acc)[8], const EdgeData& d, flo
   }
 }
 
-// Accumulate the tile's messages into `agg` (shared, [kTileNodes][200], zeroed by this function).
+// Deterministic hand-over of partial sums between the warps of a tile (DET = true).  A destination's edges are
+// contiguous, so a warp's slice consists of: possibly the TAIL of a destination an earlier warp started (its first
+// segment, when e0 > row start), then destinations it starts itself.  A started destination is written to agg[nd] by
+// plain stores -- exactly one warp starts any destination, so there is no atomic and no zero-initialisation -- and a
+// continued one into the warp's private head[warp] slot, announced in head_mask[nd] (bit = warp).  The epilogue adds
+// agg[nd] (if the row has edges) and the announced heads in ascending warp order = edge order: the sum is
+// reproducible run to run.  Without DET the partial sums are added into a zeroed agg with shared-memory atomics
+// (compiled to ATOMS.CAST.SPIN loops: ~20 % of the LSU wavefronts of the kernel, and run-to-run rounding noise).
+struct TileHeads {
+  float (*head)[200];   // [kTileWarps][200]
+  int* head_mask;       // [nodes per tile], zeroed by the caller before the barrier that precedes tile_accumulate
+};
+
+// Sum for row r, columns c, c+1 after the barrier that follows tile_accumulate (DET mode).
+__device__ __forceinline__ float2 tile_row_sum(const float (*agg)[200], const TileHeads& th, const int* s_rp, int r,
+                                               int c) {
+  float2 a = make_float2(0.f, 0.f);
+  if (s_rp[r + 1] > s_rp[r]) {
+    int m = th.head_mask[r];
+    // the starter's partial is in agg unless the row's first edge belongs to a continuation, which cannot happen:
+    // the warp holding a row's first edge is by definition its starter
+    a = *reinterpret_cast<const float2*>(&agg[r][c]);
+    while (m) {
+      const int w = __ffs(m) - 1;
+      m &= m - 1;
+      const float2 hv = *reinterpret_cast<const float2*>(&th.head[w][c]);
+      a.x += hv.x; a.y += hv.y;
+    }
+  }
+  return a;
+}
+
+// Accumulate the tile's messages into `agg` (shared, [kTileNodes][200]; zeroed by the caller unless DET).
 // s_rp: shared copy of row_ptr[v0 .. v0+nv].  EDGE_SCALE: multiply each message by scale[col_a[e]]
 // (backward: norm of the edge's destination).
-template <bool TRANSPOSE, bool INDEXED, bool EDGE_SCALE, bool STREAM_X = true>
+template <bool TRANSPOSE, bool INDEXED, bool EDGE_SCALE, bool STREAM_X = true, bool DET = false>
 __device__ __forceinline__ void tile_accumulate(float (*agg)[200], const int* s_rp, int nv,
                                                 const float* __restrict__ X, const int32_t* __restrict__ x_index,
                                                 const float* __restrict__ W, const int32_t* __restrict__ col_a,
                                                 const int32_t* __restrict__ col_type,
-                                                const float* __restrict__ scale) {
+                                                const float* __restrict__ scale, TileHeads th = TileHeads{nullptr, nullptr}) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool active = lane < 25;
   const int ebeg = s_rp[0], eend = s_rp[nv];
@@ -100,12 +132,24 @@ __device__ __forceinline__ void tile_accumulate(float (*agg)[200], const int* s_
   int node = 0;
   while (s_rp[node + 1] <= e0) ++node;
   int node_end = s_rp[node + 1];
+  bool continued = DET && e0 > s_rp[node];    // the first segment finishes a destination an earlier warp started
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 
   auto flush = [&](int nd) {
-    if (active) {
+    if (DET) {
+      float* dst = continued ? th.head[warp] : agg[nd];
+      if (continued && lane == 0) atomicOr(th.head_mask + nd, 1 << warp);
+      continued = false;
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          *reinterpret_cast<float2*>(dst + 2 * (lane + 25 * k)) = make_float2(acc[2 * k], acc[2 * k + 1]);
+          acc[2 * k] = acc[2 * k + 1] = 0.f;
+        }
+      }
+    } else if (active) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         atomicAdd(&agg[nd][2 * (lane + 25 * k)], acc[2 * k]);

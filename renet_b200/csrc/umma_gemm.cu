@@ -20,6 +20,9 @@
 //   * accumulator: 128 lanes x 208 fp32 columns of TMEM (256 allocated); epilogue reads it with
 //     tcgen05.ld 32x32b (thread = row) and writes C with bias / accumulate applied.
 #include "common.cuh"
+#include <mutex>
+#include <vector>
+
 #include "umma.cuh"
 
 namespace renet {
@@ -454,6 +457,57 @@ static uint8_t* g_scratch = nullptr;
 static int64_t g_scratch_bytes = 0;
 void set_scratch(void* p, int64_t bytes) { g_scratch = (uint8_t*)p; g_scratch_bytes = p ? bytes : 0; }
 
+// ---- packed-weight cache (renet_set_weight_generation) ------------------------------------------------------------------
+// Packing a weight into the UMMA operand image is a kernel launch per weight per call.  Weights only change when the
+// optimiser steps, so the caller may declare a "weight generation": while it is unchanged, a packed image made for a
+// given (device, pointers, shape) key is valid and reused; a new generation invalidates every image (the buffers are
+// kept and overwritten by the next pack).  generation < 0 (the default) turns the cache off.
+namespace {
+struct PackEntry {
+  int device;
+  const void* keys[6];
+  int nkeys;
+  int64_t bytes;
+  void* buf;
+  int64_t gen;
+};
+std::mutex g_pack_mu;
+std::vector<PackEntry> g_pack_entries;
+int64_t g_weight_generation = -1;
+}  // namespace
+
+void set_weight_generation(int64_t g) {
+  std::lock_guard<std::mutex> lk(g_pack_mu);
+  g_weight_generation = g;
+}
+
+void* packed_cache_lookup(const void* const* keys, int nkeys, int64_t bytes, bool* hit) {
+  *hit = false;
+  std::lock_guard<std::mutex> lk(g_pack_mu);
+  if (g_weight_generation < 0 || nkeys > 6) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  for (auto& e : g_pack_entries) {
+    if (e.device != dev || e.nkeys != nkeys || e.bytes != bytes) continue;
+    bool same = true;
+    for (int i = 0; i < nkeys; ++i) same &= e.keys[i] == keys[i];
+    if (!same) continue;
+    *hit = e.gen == g_weight_generation;
+    e.gen = g_weight_generation;
+    return e.buf;
+  }
+  if (g_pack_entries.size() >= 64) {       // bounded: drop the oldest image
+    cudaFree(g_pack_entries.front().buf);
+    g_pack_entries.erase(g_pack_entries.begin());
+  }
+  PackEntry e{};
+  e.device = dev; e.nkeys = nkeys; e.bytes = bytes; e.gen = g_weight_generation;
+  for (int i = 0; i < nkeys; ++i) e.keys[i] = keys[i];
+  if (cudaMalloc(&e.buf, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  g_pack_entries.push_back(e);
+  return e.buf;
+}
+
 // ---- building blocks shared with gru.cu ------------------------------------------------------------------------
 int64_t umma_packed_bytes(int N, int K) {
   return (int64_t)((N + UN - 1) / UN) * ((K + P_BK - 1) / P_BK) * P_B_CHUNK;
@@ -499,9 +553,14 @@ int umma_gemm_nn_try(const float* A, const int32_t* a_index, int64_t lda, const 
   // ---- packed path: needs the registered scratch buffer for the packed copy of B ---------------------------------
   if (aligned && umma_shape_ok(N, K) && (lda % 4 == 0) && (ldc % 4 == 0) && M >= 64 && g_scratch != nullptr &&
       umma_packed_bytes(N, K) <= g_scratch_bytes && (reinterpret_cast<uintptr_t>(g_scratch) & 127) == 0) {
-    int rc = umma_pack_b(B, ldb, 1, N, K, g_scratch, 0, stream);
+    bool hit = false;
+    const void* keys[4] = {B, reinterpret_cast<const void*>((intptr_t)ldb), reinterpret_cast<const void*>((intptr_t)N),
+                           reinterpret_cast<const void*>((intptr_t)K)};
+    void* cached = packed_cache_lookup(keys, 4, umma_packed_bytes(N, K), &hit);
+    void* Bp = cached ? cached : g_scratch;
+    int rc = hit ? 0 : umma_pack_b(B, ldb, 1, N, K, Bp, 0, stream);
     if (rc) return rc;
-    rc = umma_gemm_prepacked(A, a_index, lda, g_scratch, C, ldc, bias, M, N, K, accumulate, 1, 0, 0, 0, stream);
+    rc = umma_gemm_prepacked(A, a_index, lda, Bp, C, ldc, bias, M, N, K, accumulate, 1, 0, 0, 0, stream);
     return rc ? rc : 1;
   }
   const bool ok = (K % UKC == 0) && K >= UKC && (N % 8 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) &&

@@ -169,6 +169,33 @@ class BatchedHistoryGraph:
         g.comp, g.G = None, 0
         return g
 
+    # ---- edge count: known on the host for host-assembled batches; for device-assembled ones (hoststore, device
+    # batcher) it is produced on the GPU and read back lazily, so nothing on the forward path waits for it ------------
+    _E = None
+    _E_pending = None       # (event, pinned int32[1], release callback) of the asynchronous read-back
+    E_cap = None            # capacity of the col_* arrays (>= E); launch argument while E is still in flight
+
+    @property
+    def E(self):
+        if self._E is None:
+            ev, pinned, release = self._E_pending
+            ev.synchronize()
+            self._E = int(pinned[0])
+            self._E_pending = None
+            if release is not None:
+                release(pinned)
+            self.col_src, self.col_type_s, self.col_type_o = (x[:self._E] for x in (self.col_src, self.col_type_s, self.col_type_o))
+        return self._E
+
+    @E.setter
+    def E(self, v):
+        self._E = int(v)
+
+    @property
+    def E_launch(self):
+        """E when it is known without waiting, else the capacity bound (the kernels walk row_ptr, not E)."""
+        return self._E if self._E is not None else self.E_cap
+
     def number_of_nodes(self):
         return self.N
 

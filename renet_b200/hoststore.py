@@ -51,6 +51,17 @@ class GraphStore:
         self.type_o = cat([g.type_o for g in graphs], np.int32)
         self.graphs = graphs
         self.num_types = int(max(self.type_s.max(), self.type_o.max())) + 1 if len(self.type_s) else 1
+        self._dev = {}
+
+    def device_arrays(self, device):
+        """The store's edge arrays resident in HBM (uploaded once per device): what renet_induce_edges filters."""
+        key = str(torch.device(device))
+        d = self._dev.get(key)
+        if d is None:
+            up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)      # noqa: E731
+            d = self._dev[key] = dict(edge_off=up(self.edge_off), src=up(self.src), dst=up(self.dst), type_s=up(self.type_s),
+                                      type_o=up(self.type_o))
+        return d
 
     def __getitem__(self, t):
         return self.graph_dict[t]
@@ -182,17 +193,125 @@ def split_raw(buf, r):
     return out
 
 
-def _stage(view, buf_holder, sort):
-    """Host part: run the C++ batcher into a pinned buffer (grows it when needed).  Thread-safe per buffer."""
-    r = assemble_view_raw(view, buf_holder[0].numpy(), sort)
+def plan_view_raw(view, out, sort=True):
+    """Host half of the device batcher (renet_host_plan_batch) into the int32 numpy buffer ``out``."""
+    L = _lib.lib()
+    hs, gs = view.store, view.store.gs
+    B = len(view.sample_idx)
+    s_idx = np.empty(B, dtype=np.int64)
+    bsz = np.zeros(MAX_LEN, dtype=np.int32)
+    sizes = np.zeros(10, dtype=np.int64)
+    rc = L.renet_host_plan_batch(
+        len(gs.times), _p(gs.node_off), _p(gs.node_ent), _p(gs.edge_off), _p(hs.samp_off), _p(hs.samp_entry), _p(hs.ent_graph),
+        _p(hs.ent_srow), _p(hs.ent_off), _p(hs.nbr_row), _p(view.sample_idx), B, int(sort), _p(s_idx), _p(out), out.size,
+        _p(bsz), MAX_LEN, _p(sizes))
+    if rc == 1:
+        return {'need_words': int(sizes[6])}
+    _lib.check(rc, 'renet_host_plan_batch')
+    N, E_cand, S, Q, G, max_len, words, M = (int(x) for x in sizes[:8])
+    return dict(N=N, E_cand=E_cand, S=S, Q=Q, G=G, max_len=max_len, words=words, M=M, s_idx=s_idx,
+                batch_sizes=bsz[:max_len].copy(), B=B, plan=True)
+
+
+def split_plan(buf, r):
+    """Views into a staged plan buffer, in the layout renet_host_plan_batch documents."""
+    o = 0
+    out = {}
+    for name, n in (('newid', r['M']), ('node_ent', r['N']), ('readout', r['S']), ('row_comp', r['S']), ('row_seq', r['S']),
+                    ('seq_start', r['Q']), ('seq_len', r['Q']), ('packed_row', r['S']), ('s_idx', r['B']),
+                    ('comp_graph', r['G']), ('mark_off', r['G'] + 1), ('cand_off', r['G'] + 1)):
+        out[name] = buf[o:o + n]
+        o += n
+    return out
+
+
+_E_PINNED = __import__('collections').deque()       # pool of pinned int32[1] read-back slots
+
+
+def _upload_plan(view, buf, r, device):
+    """Device part of the device batcher (caller's thread / current stream): one pinned H2D copy of the plan, then
+    renet_induce_edges builds the CSR on the GPU from the resident graph store; the edge count comes back
+    asynchronously (graph.E resolves it on demand)."""
+    hb = HistoryBatch()
+    hb.s_idx, hb.num_seq, hb.S = r['s_idx'], r['Q'], r['S']
+    if r['S'] == 0:
+        hb.graph, hb.seq_len = None, np.zeros(0, np.int64)
+        return hb, None
+    L = _lib.lib()
+    gs = view.store.gs
+    ga = gs.device_arrays(device)
+    words, N, E_cand = r['words'], r['N'], r['E_cand']
+    dev = buf[:words].to(device, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    d = split_plan(dev, r)
+    h = split_plan(buf.numpy(), r)
+    ws_bytes = int(L.renet_induce_workspace_bytes(E_cand))
+    # one allocation: row_ptr[N+1] col_src col_type_s col_type_o [E_cand each] norm[N] e_count[1] + workspace
+    blob = torch.empty(N + 1 + 3 * E_cand + N + 1 + ws_bytes // 4 + 64, dtype=torch.int32, device=device)
+    o = 0
+    parts = {}
+    for name, n in (('row_ptr', N + 1), ('col_src', E_cand), ('col_type_s', E_cand), ('col_type_o', E_cand), ('norm', N),
+                    ('e_count', 1)):
+        parts[name] = blob[o:o + n]
+        o += n
+    o = (o + 63) // 64 * 64                      # 256-byte aligned workspace
+    ws = blob[o:]
+    P = _lib.ptr
+    rc = L.renet_induce_edges(P(ga['edge_off']), P(ga['src']), P(ga['dst']), P(ga['type_s']), P(ga['type_o']),
+                              P(d['comp_graph']), P(d['mark_off']), P(d['cand_off']), P(d['newid']), r['G'], N, E_cand,
+                              P(parts['row_ptr']), P(parts['col_src']), P(parts['col_type_s']), P(parts['col_type_o']),
+                              P(parts['norm']), P(parts['e_count']), P(ws), ws.numel() * 4, _lib.stream())
+    _lib.check(rc, 'renet_induce_edges')
+    try:
+        e_host = _E_PINNED.pop()
+    except IndexError:
+        e_host = torch.empty(1, dtype=torch.int32).pin_memory()
+    e_host.copy_(parts['e_count'], non_blocking=True)
+    e_ev = torch.cuda.Event()
+    e_ev.record()
+    g = BatchedHistoryGraph.__new__(BatchedHistoryGraph)
+    g.device, g.N = torch.device(device), N
+    g._E_pending, g.E_cap = (e_ev, e_host, _E_PINNED.append), E_cand
+    g.node_ent, g.row_ptr = d['node_ent'], parts['row_ptr']
+    g.col_src, g.col_type_s, g.col_type_o = parts['col_src'], parts['col_type_s'], parts['col_type_o']
+    g.norm = parts['norm'].view(torch.float32)
+    g.comp_sizes = None
+    g.h2d_bytes = words * 4
+    g.ndata = _Frame(norm=g.norm.view(-1, 1), id=g.node_ent.view(-1, 1))
+    g.h_index = g.h_table = None
+    g._bwd = {}
+    g.G, g.comp = r['G'], None
+    g.seq_len_dev = d['seq_len']
+    g._keep = (blob, dev)
+    hb.graph = g
+    hb.readout, hb.row_glob, hb.row_seq = d['readout'], d['row_comp'], d['row_seq']
+    hb.seq_start, hb.packed_row = d['seq_start'], d['packed_row']
+    hb.readout_host = h['readout'].astype(np.int64)
+    hb.seq_len = h['seq_len'].astype(np.int64)
+    hb.batch_sizes = r['batch_sizes']
+    hb.times = gs.times[h['comp_graph']]
+    hb.h2d_bytes = words * 4
+    hb.s_idx_dev, hb.comp_graph_dev = d['s_idx'], d['comp_graph']
+    hb.graph_store = gs
+    return hb, ev
+
+
+def _stage(view, buf_holder, sort, device_edges=False):
+    """Host part: run the C++ batcher (or, with device_edges, only its planning half) into a pinned buffer (grows it
+    when needed).  Thread-safe per buffer."""
+    fn = plan_view_raw if device_edges else assemble_view_raw
+    r = fn(view, buf_holder[0].numpy(), sort)
     if 'need_words' in r:
         buf_holder[0] = torch.empty(int(r['need_words'] * 1.5), dtype=torch.int32).pin_memory()
-        r = assemble_view_raw(view, buf_holder[0].numpy(), sort)
+        r = fn(view, buf_holder[0].numpy(), sort)
     return r
 
 
 def _upload(view, buf, r, device):
     """Device part (caller's thread / current stream): one pinned H2D copy, then slice it into the batch."""
+    if r.get('plan'):
+        return _upload_plan(view, buf, r, device)
     hb = HistoryBatch()
     hb.s_idx, hb.num_seq, hb.S = r['s_idx'], r['Q'], r['S']
     if r['S'] == 0:
@@ -231,27 +350,35 @@ def _upload(view, buf, r, device):
     return hb, ev
 
 
-def assemble_view(view, device, sort=True):
-    """HistoryView -> HistoryBatch on ``device`` through the C++ batcher (one pinned H2D copy)."""
+DEVICE_EDGES = True      # build the batched CSR on the GPU (renet_induce_edges); False = all-host C++ batcher
+
+
+def assemble_view(view, device, sort=True, device_edges=None):
+    """HistoryView -> HistoryBatch on ``device``: host plan + one pinned H2D copy + renet_induce_edges on the GPU
+    (default), or the all-host C++ batcher + one pinned H2D copy (device_edges=False)."""
+    if device_edges is None:
+        device_edges = DEVICE_EDGES
     st = _staging.get(str(device))
     if st is None:
         st = _staging[str(device)] = _Staging()
     slot, buf = st.next()
     holder = [buf]
-    r = _stage(view, holder, sort)
+    r = _stage(view, holder, sort, device_edges)
     st.bufs[slot] = holder[0]
     hb, ev = _upload(view, holder[0], r, device)
     st.events[slot] = ev
     return hb
 
 
-def prefetch(view_groups, device, depth=2, workers=4, sort=True, inner_threads=None):
+def prefetch(view_groups, device, depth=2, workers=4, sort=True, inner_threads=None, device_edges=None):
     """Pipeline the host batching: ``view_groups`` is an iterable of tuples of HistoryViews (one tuple per step,
     e.g. (subject view, object view)); yields tuples of HistoryBatches on ``device``.  While the consumer runs
     step i on the GPU, worker threads run the C++ batcher (which releases the GIL) for steps i+1 .. i+depth into
     their own pinned staging buffers; the H2D copy is issued from the consumer's thread on its current stream."""
     import collections
     from concurrent.futures import ThreadPoolExecutor
+    if device_edges is None:
+        device_edges = DEVICE_EDGES
     prev_threads = None
     if inner_threads is not None:          # many concurrent batcher calls: fewer threads inside each
         prev_threads = _lib.lib().renet_set_host_threads(int(inner_threads))
@@ -265,7 +392,7 @@ def prefetch(view_groups, device, depth=2, workers=4, sort=True, inner_threads=N
         except IndexError:
             buf = torch.empty(1 << 21, dtype=torch.int32).pin_memory()
         holder = [buf]
-        return view, holder, _stage(view, holder, sort)
+        return view, holder, _stage(view, holder, sort, device_edges)
 
     with ThreadPoolExecutor(max_workers=workers) as pool:
         def submit():

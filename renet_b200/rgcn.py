@@ -97,7 +97,7 @@ class _GatherFn(torch.autograd.Function):
         else:
             rc = L.renet_rgcn_gather(_lib.ptr(H), _lib.ptr(h_index), _lib.ptr(W), _lib.ptr(g.row_ptr),
                                      _lib.ptr(g.col_src), _lib.ptr(g.col_type(reverse)), _lib.ptr(g.norm),
-                                     _lib.ptr(out), g.N, g.E, d_in, d_out, num_bases, W.shape[0], int(relu),
+                                     _lib.ptr(out), g.N, g.E_launch, d_in, d_out, num_bases, W.shape[0], int(relu),
                                      int(loop is not None), _lib.stream())
             _lib.check(rc, 'renet_rgcn_gather')
         ctx.save_for_backward(H, W, out)

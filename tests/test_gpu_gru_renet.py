@@ -178,3 +178,33 @@ def test_prefetched_batches_equal_direct_assembly():
         assert torch.equal(hb.readout, ref.readout) and torch.equal(hb.packed_row, ref.packed_row)
         np.testing.assert_array_equal(hb.s_idx, ref.s_idx)
         np.testing.assert_array_equal(hb.batch_sizes, ref.batch_sizes)
+
+
+def test_packed_weight_cache_tracks_in_place_updates():
+    """The tcgen05 engine caches packed weights per (module, addresses, in-place versions): repeated encodes reuse the
+    images, an in-place update (what an optimiser step is) re-packs, and the result equals a fresh module's."""
+    import copy
+    from renet_b200 import _lib
+    b, m, params, glob, gd, batch, sh, oh, quads, sel, dims = _setup('renet_icews18_slice.npz')
+    m.eval()
+
+    def run(model):
+        with torch.no_grad():
+            return [torch.cat(model.encode(batch, sh, oh, gd, subject=subj)[3:5], 1).clone() for subj in (True, False)]
+    n0 = _lib.launch_count()
+    a1 = run(m)
+    n1 = _lib.launch_count()
+    a2 = run(m)
+    n2 = _lib.launch_count()
+    assert all(torch.equal(x, y) for x, y in zip(a1, a2))
+    assert n2 - n1 < n1 - n0                                   # the second pass skipped the packing launches
+    with torch.no_grad():
+        m.encoder.weight_hh_l0.mul_(1.25)
+        m.aggregator.rgcn2.loop_weight.add_(0.01)
+    a3 = run(m)
+    assert not torch.equal(a3[0], a1[0])
+    fresh = copy.deepcopy(m)
+    fresh.aggregator._pack_token = _lib.new_pack_token()
+    fresh.global_emb = m.global_emb
+    a4 = run(fresh)
+    assert all(torch.equal(x, y) for x, y in zip(a3, a4))

@@ -152,3 +152,54 @@ def test_cpp_batcher_matches_numpy_path():
     view = hs.select(np.asarray([0, 1]))
     r = hoststore.assemble_view_raw(view, np.zeros(64, np.int32))
     assert r['S'] == 0 and r['N'] == 0
+
+
+def _induce_numpy(gs, p):
+    """numpy statement of what renet_induce_edges computes from a plan (candidate filter + CSR)."""
+    src, ts, to, dst = [], [], [], []
+    for c in range(len(p['comp_graph'])):
+        g = int(p['comp_graph'][c])
+        lo, hi = gs.edge_off[g], gs.edge_off[g + 1]
+        assert p['cand_off'][c + 1] - p['cand_off'][c] == hi - lo
+        m = p['newid'][p['mark_off'][c]:p['mark_off'][c + 1]]
+        s, d = m[gs.src[lo:hi]], m[gs.dst[lo:hi]]
+        keep = (s >= 0) & (d >= 0)
+        src.append(s[keep]); dst.append(d[keep]); ts.append(gs.type_s[lo:hi][keep]); to.append(gs.type_o[lo:hi][keep])
+    src, dst, ts, to = (np.concatenate(x) for x in (src, dst, ts, to))
+    N = len(p['node_ent'])
+    assert np.all(np.diff(dst) >= 0)                   # survivors are already sorted by batched destination
+    row_ptr = np.searchsorted(dst, np.arange(N + 1)).astype(np.int32)
+    deg = np.diff(row_ptr).astype(np.float32)
+    return dict(row_ptr=row_ptr, col_src=src, col_type_s=ts, col_type_o=to, norm=np.float32(1) / np.maximum(deg, 1))
+
+
+def test_plan_batch_plus_induce_matches_cpp_batcher():
+    """renet_host_plan_batch (host half of the device batcher) + the induced-edge filter (numpy statement of
+    renet_induce_edges here; the CUDA kernels are compared in tests/test_gpu_device_batch.py) == renet_host_assemble_batch."""
+    from renet_b200 import hoststore
+    quads, num_e, num_r = synthetic.make_quads('icews18', seed=11, num_timestamps=16)
+    S, ST, O, OT = synthetic.build_history(quads)
+    gs = hoststore.GraphStore(synthetic.build_graph_dict(quads, num_r))
+    sel = np.random.RandomState(1).permutation(len(quads))[:300]
+    for hist, hist_t, col in ((S, ST, 0), (O, OT, 2)):
+        view = hoststore.HistoryStore(hist, hist_t, quads[:, col], gs).select(sel)
+        r = hoststore.assemble_view_raw(view, np.zeros(8, np.int32))
+        buf = np.zeros(r['need_words'], dtype=np.int32)
+        r = hoststore.assemble_view_raw(view, buf)
+        ref = hoststore.split_raw(buf, r)
+        pr = hoststore.plan_view_raw(view, np.zeros(8, np.int32))
+        assert 'need_words' in pr
+        pbuf = np.zeros(pr['need_words'], dtype=np.int32)
+        pr = hoststore.plan_view_raw(view, pbuf)
+        p = hoststore.split_plan(pbuf, pr)
+        assert (pr['N'], pr['S'], pr['Q'], pr['G']) == (r['N'], r['S'], r['Q'], r['G']) and pr['E_cand'] >= r['E']
+        np.testing.assert_array_equal(pr['s_idx'], r['s_idx'])
+        np.testing.assert_array_equal(pr['batch_sizes'], r['batch_sizes'])
+        for k in ('node_ent', 'readout', 'row_comp', 'row_seq', 'seq_start', 'seq_len', 'packed_row', 's_idx', 'comp_graph'):
+            np.testing.assert_array_equal(p[k], ref[k], err_msg=k)
+        ind = _induce_numpy(gs, p)
+        for k in ('row_ptr', 'col_src', 'col_type_s', 'col_type_o'):
+            np.testing.assert_array_equal(ind[k], ref[k], err_msg=k)
+        np.testing.assert_array_equal(ind['norm'], ref['norm'].view(np.float32))
+    pr = hoststore.plan_view_raw(view.store.select(np.asarray([0, 1])), np.zeros(64, np.int32))
+    assert pr['S'] == 0 and pr['N'] == 0
