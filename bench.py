@@ -357,12 +357,18 @@ def run_ours(args):
                     s, r, o, s_h, s_q, _ = model.encode(batch, hbs[0], hbs[1], gstore, subject=subj)
                     outs.append(torch.cat((s_h, s_q), 1))
             res = torch.cat(outs)
-            out_pinned[:res.shape[0]].copy_(res, non_blocking=True)      # D2H of this step's GRU outputs
-            ev = torch.cuda.Event()
-            ev.record()
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(copy_stream):                         # D2H of this step's GRU outputs on its own
+                copy_stream.wait_event(done)                             # stream: overlaps the next step's kernels
+                out_pinned[:res.shape[0]].copy_(res, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            res.record_stream(copy_stream)
             return h2d, res.numel() * 4, ev
 
         out_ring = [torch.empty(2 * BATCH, 2 * H_DIM).pin_memory() for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
         for e in pool:
             e['q_pinned'] = torch.from_numpy(e['q']).pin_memory()
 

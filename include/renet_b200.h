@@ -291,6 +291,36 @@ int renet_induce_edges(const int64_t* g_edge_off, const int32_t* g_src, const in
                        int32_t* col_type_o, float* norm, int32_t* e_count, void* workspace,
                        int64_t workspace_bytes, void* stream);
 
+/* Native loader: a pool of C++ worker threads that run renet_host_plan_batch / renet_host_assemble_batch jobs ahead of
+ * the consumer (the reference builds every batch synchronously inside forward(), utils.py:209-244).  submit returns a
+ * ticket (>= 0); every pointer passed must stay valid until renet_loader_wait returns for that ticket; wait blocks
+ * until the job has run and returns the job's return code.  Jobs start in submission order. */
+void* renet_loader_create(int32_t n_threads);
+void renet_loader_destroy(void* loader);
+int64_t renet_loader_submit_plan(
+    void* loader, int64_t T, const int64_t* g_node_off, const int32_t* g_node_ent, const int64_t* g_edge_off,
+    const int64_t* h_samp_off, const int64_t* h_samp_entry, const int32_t* h_ent_graph, const int32_t* h_ent_srow,
+    const int64_t* h_ent_off, const int32_t* h_nbr_row, const int64_t* sample_idx, int64_t B, int32_t sort,
+    int64_t* s_idx_out, int32_t* out, int64_t out_capacity, int32_t* batch_sizes_out, int32_t max_len_capacity,
+    int64_t* sizes);
+int64_t renet_loader_submit_assemble(
+    void* loader, int64_t T, const int64_t* g_node_off, const int32_t* g_node_ent, const int64_t* g_edge_off,
+    const int32_t* g_src, const int32_t* g_dst, const int32_t* g_type_s, const int32_t* g_type_o,
+    const int64_t* h_samp_off, const int64_t* h_samp_entry, const int32_t* h_ent_graph, const int32_t* h_ent_srow,
+    const int64_t* h_ent_off, const int32_t* h_nbr_row, const int64_t* sample_idx, int64_t B, int32_t sort, int32_t R2,
+    int32_t n_hot_max, int64_t* s_idx_out, int32_t* out, int64_t out_capacity, int32_t* comp_graph_out,
+    int32_t* batch_sizes_out, int32_t max_len_capacity, int64_t* sizes);
+int renet_loader_wait(void* loader, int64_t ticket);
+
+/* Sequence ids of a batch in processing order, on the device, in one launch (model.py:81-84, utils.py:224-225):
+ *   seq_s[q] = triplets[s_idx[q]][col_s], seq_r[q] = triplets[s_idx[q]][1]   for q < Q   (triplets int64 [B,ld], ld >= 3;
+ *   col_s = 0 for the subject direction, 2 for the object direction; s_idx = renet_host_*_batch's sample order)
+ *   row_graph[i] = comp_graph[row_comp[i]]                                    for i < S   (graph-store index of the
+ *   timestamp of every read-out row: indexes a dense [T_all,h] table of the global embeddings) */
+int renet_prepare_sequences(const int64_t* triplets, int32_t ld, int32_t col_s, const int32_t* s_idx, int64_t Q,
+                            const int32_t* comp_graph, const int32_t* row_comp, int64_t S, int32_t* seq_s,
+                            int32_t* seq_r, int32_t* row_graph, void* stream);
+
 /* One call for the whole forward hot path of one direction (inference / no autograd):
  *   H1 = relu-layer(ent[node_ent]), H2 = linear-layer(H1)   (renet_rgcn_block_fwd x2, Aggregator.py:136-137)
  *   hn4, hn3 = renet_gru_fwd(H2, ...)                          (Aggregator.py:139-165 + model.py:86,94)

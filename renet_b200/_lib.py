@@ -43,6 +43,12 @@ SIGNATURES = {
     'renet_induce_edges': (ctypes.c_int, [_vp] * 9 + [_i64, _i64, _i64] + [_vp] * 7 + [_i64, _vp]),
     'renet_encode_fwd': (ctypes.c_int, [_vp] * 12 + [_i64, _i64, _i32] + [_vp] * 9 + [_i32] + [_vp] * 10 +
                          [_i64, _i64, _i64, _i32, _i32, _vp, _i64, _vp]),
+    'renet_loader_create': (_vp, [_i32]),
+    'renet_loader_destroy': (None, [_vp]),
+    'renet_loader_submit_plan': (_i64, [_vp, _i64] + [_vp] * 10 + [_i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp]),
+    'renet_loader_submit_assemble': (_i64, [_vp, _i64] + [_vp] * 13 + [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
+    'renet_loader_wait': (ctypes.c_int, [_vp, _i64]),
+    'renet_prepare_sequences': (ctypes.c_int, [_vp, _i32, _i32, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'renet_pack_inputs': (ctypes.c_int, [_vp] * 12 + [_i64, _i32, _vp]),
 }
 

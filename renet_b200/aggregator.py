@@ -132,8 +132,10 @@ class RGCNAggregator(nn.Module):
         return p4.data, p3.data          # a single sequence: packed order == time order
 
     # ---------------------------------------------------------------------------------------------
-    def encode(self, hist, s, r, ent_embeds, rel_embeds, graph_dict, global_emb, reverse, encoder, encoder_r):
-        """history -> RGCN x2 -> fused read-out + both GRUs.  Returns (s_h [Q,h], s_q [Q,h], hb)."""
+    def encode(self, hist, s, r, ent_embeds, rel_embeds, graph_dict, global_emb, reverse, encoder, encoder_r, triplets=None):
+        """history -> RGCN x2 -> fused read-out + both GRUs.  Returns (s_h, s_q, hb) with Q rows (non-empty histories,
+        length-sorted), or already zero-padded to len(s) rows on the no-autograd path.  ``triplets`` (optional, the int64
+        [B,3] batch s and r are columns of) lets that path build the sequence ids in one launch."""
         from .gru import fused_gru
         dev = ent_embeds.device
         hb = self._batch(hist, s, graph_dict, dev, True)
@@ -143,38 +145,55 @@ class RGCNAggregator(nn.Module):
                    encoder_r.weight_ih_l0, encoder_r.weight_hh_l0]
         with _lib.weight_generation(self._pack_token, weights):
             if not torch.is_grad_enabled() and not self.training:
-                return self._encode_inference(hb, s, r, ent_embeds, rel_embeds, global_emb, reverse, encoder, encoder_r)
+                return self._encode_inference(hb, s, r, ent_embeds, rel_embeds, global_emb, reverse, encoder, encoder_r, triplets)
             H2 = self.aggregate(hb, ent_embeds, reverse)
             glob = global_rows_of_batch(global_emb, hb, self.h_dim, dev)
             _, _, seq_s, seq_r = self._sorted_ids(hb, s, r, dev)
             s_h, s_q = fused_gru(H2, ent_embeds, rel_embeds, glob, hb, seq_s, seq_r, encoder, encoder_r)
             return s_h, s_q, hb
 
-    def _encode_inference(self, hb, s, r, ent_embeds, rel_embeds, global_emb, reverse, encoder, encoder_r):
+    def _encode_inference(self, hb, s, r, ent_embeds, rel_embeds, global_emb, reverse, encoder, encoder_r, triplets=None):
         """No-autograd fast path: the whole direction (2 RGCN layers + read-out + both GRUs) is ONE C-ABI call
-        (renet_encode_fwd), so the Python cost per direction is a handful of tensor ops instead of ~60."""
+        (renet_encode_fwd), so the Python cost per direction is a handful of tensor ops instead of ~60.  Returns the GRU
+        states zero-padded to len(s) rows (model.py:88,96)."""
         from .gru import _gru_params
+        from .utils import _global_table
         L = _lib.lib()
+        P = _lib.ptr
         dev = ent_embeds.device
         g, h = hb.graph, self.h_dim
-        glob = global_rows_of_batch(global_emb, hb, h, dev)
-        idx = hb.sample_order(dev)
-        Q = hb.num_seq
-        seq_s = s.reshape(-1)[idx][:Q].to(torch.int32)
-        seq_r = r.reshape(-1)[idx][:Q].to(torch.int32)
+        Q, B = hb.num_seq, s.numel()
+        cg, gs = getattr(hb, 'comp_graph_dev', None), getattr(hb, 'graph_store', None)
+        fast = (triplets is not None and cg is not None and gs is not None and triplets.dtype == torch.int64 and
+                triplets.is_cuda and triplets.is_contiguous() and triplets.dim() == 2 and triplets.shape[1] >= 3)
+        if fast:
+            table, keys = _global_table(global_emb, h, dev)
+            fast = len(keys) == len(gs.times) and (keys is gs.times or np.array_equal(keys, gs.times))
+        if fast:
+            # sequence ids and the read-out rows' global-table index in one launch (renet_prepare_sequences)
+            ids = torch.empty(2 * Q + hb.S, dtype=torch.int32, device=dev)
+            seq_s, seq_r, row_glob = ids[:Q], ids[Q:2 * Q], ids[2 * Q:]
+            _lib.check(L.renet_prepare_sequences(P(triplets), triplets.shape[1], 2 if reverse else 0, P(hb.s_idx_dev), Q, P(cg), P(hb.row_glob),
+                                                 hb.S, P(seq_s), P(seq_r), P(row_glob), _lib.stream()), 'renet_prepare_sequences')
+            glob = table
+        else:
+            glob = global_rows_of_batch(global_emb, hb, h, dev)
+            idx = hb.sample_order(dev)
+            seq_s = s.reshape(-1)[idx][:Q].to(torch.int32)
+            seq_r = r.reshape(-1)[idx][:Q].to(torch.int32)
+            row_glob = hb.row_glob
         p4, p3 = _gru_params(encoder), _gru_params(encoder_r)
         rel = rel_embeds.contiguous()
         T = glob.shape[0]
         H = torch.empty(2, g.N, h, device=dev)
-        hn = torch.zeros(2, Q, h, device=dev)
+        hn = torch.zeros(2, B, h, device=dev)          # rows >= Q stay zero: samples without history
         nbytes = int(L.renet_gru_workspace_bytes(hb.S, Q, T, h))
         ws = torch.empty(nbytes // 4 + 4, dtype=torch.float32, device=dev)
         bs = hb.batch_sizes
-        P = _lib.ptr
         l1, l2 = self.rgcn1, self.rgcn2
         rc = L.renet_encode_fwd(P(ent_embeds), P(g.node_ent), P(g.row_ptr), P(g.col_src), P(g.col_type(reverse)),
                                 P(g.norm), P(l1.weight), P(l1.loop_weight), P(l2.weight), P(l2.loop_weight), P(H[0]),
-                                P(H[1]), g.N, g.E_launch, l1.weight.shape[0], P(hb.readout), P(hb.row_glob), P(glob), P(rel),
+                                P(H[1]), g.N, g.E_launch, l1.weight.shape[0], P(hb.readout), P(row_glob), P(glob), P(rel),
                                 P(seq_s), P(seq_r), P(g.seq_len_dev), P(hb.seq_start),
                                 bs.ctypes.data_as(_lib.ctypes.c_void_p), len(bs), P(p4[0]), P(p4[1]), P(p4[2]), P(p4[3]),
                                 P(p3[0]), P(p3[1]), P(p3[2]), P(p3[3]), P(hn[0]), P(hn[1]), hb.S, Q, T, h, l1.num_bases,

@@ -102,6 +102,26 @@ int key_bits(int64_t N) {
 
 using namespace renet;
 
+namespace renet {
+namespace {
+// seq_s[q] = triplets[s_idx[q]][col_s], seq_r[q] = triplets[s_idx[q]][1] (model.py:81-84: samples in history-length
+// order) and row_graph[i] = comp_graph[row_comp[i]] (utils.py:224-225: the timestamp of every read-out row), one launch
+__global__ void prepare_sequences_kernel(const int64_t* __restrict__ triplets, int ld, int col_s, const int32_t* __restrict__ s_idx,
+                                         int Q, const int32_t* __restrict__ comp_graph,
+                                         const int32_t* __restrict__ row_comp, int S, int32_t* __restrict__ seq_s,
+                                         int32_t* __restrict__ seq_r, int32_t* __restrict__ row_graph) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Q) {
+    const int64_t* t = triplets + ld * (int64_t)s_idx[i];
+    seq_s[i] = (int32_t)t[col_s];
+    seq_r[i] = (int32_t)t[1];
+  }
+  if (i < S) row_graph[i] = comp_graph[row_comp[i]];
+}
+}  // namespace
+}  // namespace renet
+
+
 extern "C" {
 
 int renet_version(void) { return 100; /* 0.1.0 */ }
@@ -327,6 +347,20 @@ int renet_encode_fwd(const float* ent, const int32_t* node_ent, const int32_t* r
   return renet_gru_fwd(H2, readout, row_glob, glob, ent, rel, seq_s, seq_r, seq_len, seq_start, host_batch_sizes, max_len,
                        w_ih4, w_hh4, b_ih4, b_hh4, w_ih3, w_hh3, b_ih3, b_hh3, hn4, hn3, S, Q, T, h, workspace,
                        workspace_bytes, stream);
+}
+
+int renet_prepare_sequences(const int64_t* triplets, int32_t ld, int32_t col_s, const int32_t* s_idx, int64_t Q,
+                             const int32_t* comp_graph, const int32_t* row_comp, int64_t S, int32_t* seq_s,
+                             int32_t* seq_r, int32_t* row_graph, void* stream) {
+  RENET_CHECK_ARG(Q >= 0 && S >= 0 && (col_s == 0 || col_s == 2) && ld >= 3, "renet_prepare_sequences: bad arguments");
+  const int64_t n = Q > S ? Q : S;
+  if (n == 0) return RENET_OK;
+  RENET_CHECK_ARG((Q == 0 || (triplets && s_idx && seq_s && seq_r)) && (S == 0 || (comp_graph && row_comp && row_graph)),
+                  "renet_prepare_sequences: null pointer");
+  renet::prepare_sequences_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      triplets, ld, col_s, s_idx, (int)Q, comp_graph, row_comp, (int)S, seq_s, seq_r, row_graph);
+  RENET_CHECK_LAUNCH("prepare_sequences_kernel");
+  return RENET_OK;
 }
 
 int renet_pack_inputs(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,

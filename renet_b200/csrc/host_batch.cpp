@@ -331,3 +331,106 @@ extern "C" int renet_host_plan_batch(
   o_coff[G] = (int32_t)acc;
   return RENET_OK;
 }
+
+// ---- native loader: a pool of C++ worker threads that run batch jobs ahead of the consumer ------------------------------
+// The Python prefetcher used a ThreadPoolExecutor; its workers fought the consumer thread for the GIL around every
+// ctypes call.  Here the workers are plain C++ threads: submit() enqueues a job (the arguments of
+// renet_host_plan_batch / renet_host_assemble_batch; every pointer must stay valid until wait() returns for the
+// ticket), wait() blocks -- without the GIL, being a ctypes call -- until that job has run and returns its code.
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <unordered_map>
+
+namespace {
+struct Loader {
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done;
+  std::deque<std::pair<int64_t, std::function<int()>>> queue;
+  std::unordered_map<int64_t, int> done;
+  std::vector<std::thread> threads;
+  int64_t next_ticket = 0;
+  bool stop = false;
+
+  explicit Loader(int n) {
+    for (int i = 0; i < n; ++i) threads.emplace_back([this] { run(); });
+  }
+  ~Loader() {
+    { std::lock_guard<std::mutex> lk(mu); stop = true; }
+    cv_job.notify_all();
+    for (auto& t : threads) t.join();
+  }
+  void run() {
+    for (;;) {
+      std::pair<int64_t, std::function<int()>> job;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_job.wait(lk, [this] { return stop || !queue.empty(); });
+        if (queue.empty()) return;      // stop requested and nothing left
+        job = std::move(queue.front());
+        queue.pop_front();
+      }
+      const int rc = job.second();
+      { std::lock_guard<std::mutex> lk(mu); done[job.first] = rc; }
+      cv_done.notify_all();
+    }
+  }
+  int64_t submit(std::function<int()> f) {
+    int64_t t;
+    { std::lock_guard<std::mutex> lk(mu); t = next_ticket++; queue.emplace_back(t, std::move(f)); }
+    cv_job.notify_one();
+    return t;
+  }
+  int wait(int64_t ticket) {
+    std::unique_lock<std::mutex> lk(mu);
+    cv_done.wait(lk, [&] { return done.count(ticket) != 0; });
+    const int rc = done[ticket];
+    done.erase(ticket);
+    return rc;
+  }
+};
+}  // namespace
+
+extern "C" void* renet_loader_create(int32_t n_threads) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 64) n_threads = 64;
+  return new Loader(n_threads);
+}
+
+extern "C" void renet_loader_destroy(void* loader) { delete static_cast<Loader*>(loader); }
+
+extern "C" int64_t renet_loader_submit_plan(
+    void* loader, int64_t T, const int64_t* g_node_off, const int32_t* g_node_ent, const int64_t* g_edge_off,
+    const int64_t* h_samp_off, const int64_t* h_samp_entry, const int32_t* h_ent_graph, const int32_t* h_ent_srow,
+    const int64_t* h_ent_off, const int32_t* h_nbr_row, const int64_t* sample_idx, int64_t B, int32_t sort,
+    int64_t* s_idx_out, int32_t* out, int64_t out_capacity, int32_t* batch_sizes_out, int32_t max_len_capacity,
+    int64_t* sizes) {
+  if (!loader) return -1;
+  return static_cast<Loader*>(loader)->submit([=]() {
+    return renet_host_plan_batch(T, g_node_off, g_node_ent, g_edge_off, h_samp_off, h_samp_entry, h_ent_graph, h_ent_srow,
+                                 h_ent_off, h_nbr_row, sample_idx, B, sort, s_idx_out, out, out_capacity, batch_sizes_out,
+                                 max_len_capacity, sizes);
+  });
+}
+
+extern "C" int64_t renet_loader_submit_assemble(
+    void* loader, int64_t T, const int64_t* g_node_off, const int32_t* g_node_ent, const int64_t* g_edge_off,
+    const int32_t* g_src, const int32_t* g_dst, const int32_t* g_type_s, const int32_t* g_type_o,
+    const int64_t* h_samp_off, const int64_t* h_samp_entry, const int32_t* h_ent_graph, const int32_t* h_ent_srow,
+    const int64_t* h_ent_off, const int32_t* h_nbr_row, const int64_t* sample_idx, int64_t B, int32_t sort, int32_t R2,
+    int32_t n_hot_max, int64_t* s_idx_out, int32_t* out, int64_t out_capacity, int32_t* comp_graph_out,
+    int32_t* batch_sizes_out, int32_t max_len_capacity, int64_t* sizes) {
+  if (!loader) return -1;
+  return static_cast<Loader*>(loader)->submit([=]() {
+    return renet_host_assemble_batch(T, g_node_off, g_node_ent, g_edge_off, g_src, g_dst, g_type_s, g_type_o, h_samp_off,
+                                     h_samp_entry, h_ent_graph, h_ent_srow, h_ent_off, h_nbr_row, sample_idx, B, sort, R2,
+                                     n_hot_max, s_idx_out, out, out_capacity, comp_graph_out, batch_sizes_out,
+                                     max_len_capacity, sizes);
+  });
+}
+
+extern "C" int renet_loader_wait(void* loader, int64_t ticket) {
+  if (!loader || ticket < 0) { renet::set_error("renet_loader_wait: bad loader / ticket"); return RENET_ERR_INVALID_ARG; }
+  return static_cast<Loader*>(loader)->wait(ticket);
+}

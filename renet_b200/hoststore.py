@@ -225,7 +225,78 @@ def split_plan(buf, r):
     return out
 
 
+class NativeLoader:
+    """C++ worker threads (renet_loader_*) running batch jobs ahead of the consumer, without the GIL."""
+
+    def __init__(self, workers):
+        self.L = _lib.lib()
+        self.h = self.L.renet_loader_create(int(workers))
+        if not self.h:
+            raise RuntimeError('renet_loader_create failed')
+
+    def close(self):
+        if self.h:
+            self.L.renet_loader_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def submit(self, view, out, sort, device_edges):
+        """Enqueue the host work of one batch into the int32 numpy buffer ``out``; returns the job record that finish()
+        takes (it keeps every array the C++ job writes alive)."""
+        hs, gs = view.store, view.store.gs
+        B = len(view.sample_idx)
+        job = dict(view=view, out=out, sort=sort, device_edges=device_edges, B=B, s_idx=np.empty(B, dtype=np.int64),
+                   bsz=np.zeros(MAX_LEN, dtype=np.int32), sizes=np.zeros(10, dtype=np.int64),
+                   comp_graph=np.empty(len(gs.times), dtype=np.int32))
+        if device_edges:
+            t = self.L.renet_loader_submit_plan(
+                self.h, len(gs.times), _p(gs.node_off), _p(gs.node_ent), _p(gs.edge_off), _p(hs.samp_off), _p(hs.samp_entry),
+                _p(hs.ent_graph), _p(hs.ent_srow), _p(hs.ent_off), _p(hs.nbr_row), _p(view.sample_idx), B, int(sort),
+                _p(job['s_idx']), _p(out), out.size, _p(job['bsz']), MAX_LEN, _p(job['sizes']))
+        else:
+            t = self.L.renet_loader_submit_assemble(
+                self.h, len(gs.times), _p(gs.node_off), _p(gs.node_ent), _p(gs.edge_off), _p(gs.src), _p(gs.dst), _p(gs.type_s),
+                _p(gs.type_o), _p(hs.samp_off), _p(hs.samp_entry), _p(hs.ent_graph), _p(hs.ent_srow), _p(hs.ent_off),
+                _p(hs.nbr_row), _p(view.sample_idx), B, int(sort), gs.num_types, N_HOT, _p(job['s_idx']), _p(out), out.size,
+                _p(job['comp_graph']), _p(job['bsz']), MAX_LEN, _p(job['sizes']))
+        if t < 0:
+            raise RuntimeError('renet_loader_submit failed')
+        job['ticket'] = t
+        return job
+
+    def finish(self, job):
+        """Wait for the job; returns the dict plan_view_raw / assemble_view_raw return."""
+        rc = self.L.renet_loader_wait(self.h, job['ticket'])
+        sizes = job['sizes']
+        if rc == 1:
+            return {'need_words': int(sizes[6])}
+        _lib.check(rc, 'renet_loader job')
+        if job['device_edges']:
+            N, E_cand, S, Q, G, max_len, words, M = (int(x) for x in sizes[:8])
+            return dict(N=N, E_cand=E_cand, S=S, Q=Q, G=G, max_len=max_len, words=words, M=M, s_idx=job['s_idx'],
+                        batch_sizes=job['bsz'][:max_len].copy(), B=job['B'], plan=True)
+        N, E, S, Q, G, max_len, words = (int(x) for x in sizes[:7])
+        gs = job['view'].store.gs
+        return dict(N=N, E=E, S=S, Q=Q, G=G, max_len=max_len, words=words, s_idx=job['s_idx'],
+                    comp_graph=job['comp_graph'][:G], batch_sizes=job['bsz'][:max_len].copy(), R2=gs.num_types,
+                    n_hot_s=int(sizes[7]), n_hot_o=int(sizes[8]), B=job['B'])
+
+
 _E_PINNED = __import__('collections').deque()       # pool of pinned int32[1] read-back slots
+_LOADER_STREAMS = {}
+
+
+def _loader_stream(device):
+    key = str(torch.device(device))
+    st = _LOADER_STREAMS.get(key)
+    if st is None:
+        st = _LOADER_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
 
 
 def _upload_plan(view, buf, r, device):
@@ -241,35 +312,45 @@ def _upload_plan(view, buf, r, device):
     gs = view.store.gs
     ga = gs.device_arrays(device)
     words, N, E_cand = r['words'], r['N'], r['E_cand']
-    dev = buf[:words].to(device, non_blocking=True)
-    ev = torch.cuda.Event()
-    ev.record()
-    d = split_plan(dev, r)
-    h = split_plan(buf.numpy(), r)
-    ws_bytes = int(L.renet_induce_workspace_bytes(E_cand))
-    # one allocation: row_ptr[N+1] col_src col_type_s col_type_o [E_cand each] norm[N] e_count[1] + workspace
-    blob = torch.empty(N + 1 + 3 * E_cand + N + 1 + ws_bytes // 4 + 64, dtype=torch.int32, device=device)
-    o = 0
-    parts = {}
-    for name, n in (('row_ptr', N + 1), ('col_src', E_cand), ('col_type_s', E_cand), ('col_type_o', E_cand), ('norm', N),
-                    ('e_count', 1)):
-        parts[name] = blob[o:o + n]
-        o += n
-    o = (o + 63) // 64 * 64                      # 256-byte aligned workspace
-    ws = blob[o:]
-    P = _lib.ptr
-    rc = L.renet_induce_edges(P(ga['edge_off']), P(ga['src']), P(ga['dst']), P(ga['type_s']), P(ga['type_o']),
-                              P(d['comp_graph']), P(d['mark_off']), P(d['cand_off']), P(d['newid']), r['G'], N, E_cand,
-                              P(parts['row_ptr']), P(parts['col_src']), P(parts['col_type_s']), P(parts['col_type_o']),
-                              P(parts['norm']), P(parts['e_count']), P(ws), ws.numel() * 4, _lib.stream())
-    _lib.check(rc, 'renet_induce_edges')
-    try:
-        e_host = _E_PINNED.pop()
-    except IndexError:
-        e_host = torch.empty(1, dtype=torch.int32).pin_memory()
-    e_host.copy_(parts['e_count'], non_blocking=True)
-    e_ev = torch.cuda.Event()
-    e_ev.record()
+    # the copy and the CSR build run on a loader stream, so they overlap the previous step's kernels on the caller's
+    # stream; the caller's stream waits on `ready` before it touches the batch
+    main = torch.cuda.current_stream(device)
+    ls = _loader_stream(device)
+    with torch.cuda.stream(ls):
+        dev = buf[:words].to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(ls)
+        d = split_plan(dev, r)
+        h = split_plan(buf.numpy(), r)
+        ws_bytes = int(L.renet_induce_workspace_bytes(E_cand))
+        # one allocation: row_ptr[N+1] col_src col_type_s col_type_o [E_cand each] norm[N] e_count[1] + workspace
+        blob = torch.empty(N + 1 + 3 * E_cand + N + 1 + ws_bytes // 4 + 64, dtype=torch.int32, device=device)
+        o = 0
+        parts = {}
+        for name, n in (('row_ptr', N + 1), ('col_src', E_cand), ('col_type_s', E_cand), ('col_type_o', E_cand), ('norm', N),
+                        ('e_count', 1)):
+            parts[name] = blob[o:o + n]
+            o += n
+        o = (o + 63) // 64 * 64                      # 256-byte aligned workspace
+        ws = blob[o:]
+        P = _lib.ptr
+        rc = L.renet_induce_edges(P(ga['edge_off']), P(ga['src']), P(ga['dst']), P(ga['type_s']), P(ga['type_o']),
+                                  P(d['comp_graph']), P(d['mark_off']), P(d['cand_off']), P(d['newid']), r['G'], N, E_cand,
+                                  P(parts['row_ptr']), P(parts['col_src']), P(parts['col_type_s']), P(parts['col_type_o']),
+                                  P(parts['norm']), P(parts['e_count']), P(ws), ws.numel() * 4, _lib.stream())
+        _lib.check(rc, 'renet_induce_edges')
+        ready = torch.cuda.Event()
+        ready.record(ls)
+        try:
+            e_host = _E_PINNED.pop()
+        except IndexError:
+            e_host = torch.empty(1, dtype=torch.int32).pin_memory()
+        e_host.copy_(parts['e_count'], non_blocking=True)
+        e_ev = torch.cuda.Event()
+        e_ev.record(ls)
+    main.wait_event(ready)
+    dev.record_stream(main)          # allocated on the loader stream, consumed on the caller's
+    blob.record_stream(main)
     g = BatchedHistoryGraph.__new__(BatchedHistoryGraph)
     g.device, g.N = torch.device(device), N
     g._E_pending, g.E_cap = (e_ev, e_host, _E_PINNED.append), E_cand
@@ -370,48 +451,52 @@ def assemble_view(view, device, sort=True, device_edges=None):
     return hb
 
 
-def prefetch(view_groups, device, depth=2, workers=4, sort=True, inner_threads=None, device_edges=None):
+def prefetch(view_groups, device, depth=2, workers=4, sort=True, inner_threads=1, device_edges=None):
     """Pipeline the host batching: ``view_groups`` is an iterable of tuples of HistoryViews (one tuple per step,
     e.g. (subject view, object view)); yields tuples of HistoryBatches on ``device``.  While the consumer runs
-    step i on the GPU, worker threads run the C++ batcher (which releases the GIL) for steps i+1 .. i+depth into
-    their own pinned staging buffers; the H2D copy is issued from the consumer's thread on its current stream."""
+    step i on the GPU, native worker threads (renet_loader_*, no GIL) prepare steps i+1 .. i+depth into their own
+    pinned staging buffers; the H2D copy (and, with the device batcher, the CSR build) is issued from the consumer's
+    thread when the batch is handed over."""
     import collections
-    from concurrent.futures import ThreadPoolExecutor
     if device_edges is None:
         device_edges = DEVICE_EDGES
     prev_threads = None
     if inner_threads is not None:          # many concurrent batcher calls: fewer threads inside each
         prev_threads = _lib.lib().renet_set_host_threads(int(inner_threads))
     free = _PINNED_POOL          # pinned staging buffers are expensive to create (~4 ms each): pooled per process
+    loader = NativeLoader(workers)
     pending = collections.deque()
     it = iter(view_groups)
 
-    def job(view):
+    def start(view):
         try:
             buf = free.pop()
         except IndexError:
             buf = torch.empty(1 << 21, dtype=torch.int32).pin_memory()
-        holder = [buf]
-        return view, holder, _stage(view, holder, sort, device_edges)
+        return [buf], loader.submit(view, buf.numpy(), sort, device_edges)
 
-    with ThreadPoolExecutor(max_workers=workers) as pool:
-        def submit():
-            try:
-                grp = next(it)
-            except StopIteration:
-                return False
-            pending.append([pool.submit(job, v) for v in grp])
-            return True
+    def submit():
+        try:
+            grp = next(it)
+        except StopIteration:
+            return False
+        pending.append([start(v) for v in grp])
+        return True
+
+    try:
         for _ in range(depth):
             if not submit():
                 break
         in_flight = collections.deque()       # (event, buffer) of uploads whose pinned buffer is not reusable yet
         while pending:
-            futs = pending.popleft()
+            jobs = pending.popleft()
             out = []
-            for f in futs:
-                view, holder, r = f.result()
-                hb, ev = _upload(view, holder[0], r, device)
+            for holder, job in jobs:
+                r = loader.finish(job)
+                if 'need_words' in r:            # staging buffer too small: grow it and redo this batch synchronously
+                    holder[0] = torch.empty(int(r['need_words'] * 1.5), dtype=torch.int32).pin_memory()
+                    r = _stage(job['view'], holder, sort, device_edges)
+                hb, ev = _upload(job['view'], holder[0], r, device)
                 out.append(hb)
                 in_flight.append((ev, holder[0]))
             submit()
@@ -422,5 +507,10 @@ def prefetch(view_groups, device, depth=2, workers=4, sort=True, inner_threads=N
             if ev is not None:
                 ev.synchronize()
             free.append(buf)
-    if prev_threads is not None:
-        _lib.lib().renet_set_host_threads(prev_threads)
+    finally:
+        for jobs in pending:               # consumer stopped early: the jobs still own their buffers until they ran
+            for holder, job in jobs:
+                loader.finish(job)
+        loader.close()
+        if prev_threads is not None:
+            _lib.lib().renet_set_host_threads(prev_threads)

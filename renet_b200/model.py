@@ -75,15 +75,16 @@ class RENet(RENetInference, nn.Module):
             o, r, s = triplets[:, 0], triplets[:, 1], triplets[:, 2]
             hist, reverse = o_hist, True
         s_h, s_q, hb = self.aggregator.encode(hist, s, r, self.ent_embeds, rel_embeds, graph_dict,
-                                              self.global_emb, reverse, self.encoder, self.encoder_r)
+                                              self.global_emb, reverse, self.encoder, self.encoder_r, triplets=triplets)
         if self.training and self.aggregator.dropout.p > 0:
             # the reference drops out the GRU inputs (Aggregator.py:157-158); the fused path has no
             # materialised input to drop, so training with dropout goes through forward_unfused().
             raise RuntimeError('fused encode() does not implement input dropout; use dropout=0 or forward_unfused')
         idx = hb.sample_order(triplets.device)
-        pad = torch.zeros(len(s) - s_h.shape[0], self.h_dim, device=s_h.device)
-        s_h = torch.cat((s_h, pad), dim=0)                                # model.py:88
-        s_q = torch.cat((s_q, pad), dim=0)                                # model.py:96
+        if s_h.shape[0] < len(s):                                         # (the no-autograd path pads by itself)
+            pad = torch.zeros(len(s) - s_h.shape[0], self.h_dim, device=s_h.device)
+            s_h = torch.cat((s_h, pad), dim=0)                            # model.py:88
+            s_q = torch.cat((s_q, pad), dim=0)                            # model.py:96
         return s[idx], r[idx], o[idx], s_h, s_q, rel_embeds
 
     def decode_loss(self, s, r, o, s_h, s_q, rel_embeds):

@@ -203,3 +203,28 @@ def test_plan_batch_plus_induce_matches_cpp_batcher():
         np.testing.assert_array_equal(ind['norm'], ref['norm'].view(np.float32))
     pr = hoststore.plan_view_raw(view.store.select(np.asarray([0, 1])), np.zeros(64, np.int32))
     assert pr['S'] == 0 and pr['N'] == 0
+
+
+def test_native_loader_jobs_equal_synchronous_calls():
+    """renet_loader_* (C++ worker threads) produce the buffers of the synchronous entry points, in ticket order,
+    and report a too-small staging buffer the same way."""
+    from renet_b200 import hoststore
+    quads, num_e, num_r = synthetic.make_quads('icews18', seed=11, num_timestamps=16)
+    S, ST, O, OT = synthetic.build_history(quads)
+    gs = hoststore.GraphStore(synthetic.build_graph_dict(quads, num_r))
+    hs = hoststore.HistoryStore(S, ST, quads[:, 0], gs)
+    ld = hoststore.NativeLoader(4)
+    sels = [np.random.RandomState(i).permutation(len(quads))[:300] for i in range(6)]
+    for device_edges, sync in ((True, hoststore.plan_view_raw), (False, hoststore.assemble_view_raw)):
+        jobs = [ld.submit(hs.select(s), np.zeros(1 << 20, np.int32), True, device_edges) for s in sels]
+        for s, j in zip(sels, jobs):
+            r = ld.finish(j)
+            ref_buf = np.zeros(1 << 20, np.int32)
+            ref = sync(hs.select(s), ref_buf)
+            assert r['words'] == ref['words']
+            np.testing.assert_array_equal(j['out'][:r['words']], ref_buf[:r['words']])
+            np.testing.assert_array_equal(r['s_idx'], ref['s_idx'])
+            np.testing.assert_array_equal(r['batch_sizes'], ref['batch_sizes'])
+    small = ld.finish(ld.submit(hs.select(sels[0]), np.zeros(8, np.int32), True, True))
+    assert small == {'need_words': sync and hoststore.plan_view_raw(hs.select(sels[0]), np.zeros(8, np.int32))['need_words']}
+    ld.close()
