@@ -56,6 +56,10 @@ int renet_set_gather_variant(int variant);
  * them.  generation < 0 (default) disables the cache: weights are packed on every call.  The Python host derives the
  * generation from the parameters' identities and in-place version counters. */
 int renet_set_weight_generation(int64_t generation);
+/* Experiment knob (with renet_set_gather_variant(7)): up to 48 distinct relation-type ids (rows of the [R2, ...] block
+ * table, host array) that occur most often on edges; the fused gather then runs as a persistent kernel that keeps those
+ * rows in shared memory.  Bit-identical results; measured slower than the default kernel.  n_hot = 0 clears it. */
+int renet_set_hot_relations(const int32_t* hot_rel, int32_t n_hot, int32_t R2);
 /* Optional caller-owned DEVICE scratch buffer (128-byte aligned) the tensor-core GEMM engine uses for the packed
  * (hi/lo split, K-major, 128-byte-swizzled) copy of the B operand, so that GEMM CTAs can fetch it with TMA bulk
  * copies.  Needs ceil(N/200)*ceil(K/32)*53248 bytes per GEMM (W_loop: 373 KB; GRU input projection: 2.2 MB); without

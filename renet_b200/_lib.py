@@ -22,6 +22,7 @@ SIGNATURES = {
     'renet_get_gemm_engine': (ctypes.c_int, []),
     'renet_set_gather_variant': (ctypes.c_int, [ctypes.c_int]),
     'renet_set_weight_generation': (ctypes.c_int, [_i64]),
+    'renet_set_hot_relations': (ctypes.c_int, [_vp, _i32, _i32]),
     'renet_set_scratch': (ctypes.c_int, [_vp, _i64]),
     'renet_csr_workspace_bytes': (_i64, [_i64, _i64]),
     'renet_build_csr': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),

@@ -23,7 +23,8 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
                        const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout,
                        int64_t N, int64_t E, int d_in, int d_out, int nb, int relu, int has_loop,
-                       cudaStream_t stream);
+                       cudaStream_t stream, int R2 = -1);
+int set_hot_relations(const int32_t* hot_rel_host, int n_hot, int R2);
 int launch_rgcn_gather_comp(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
                             const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout,
                             const int32_t* comp_ptr, const int32_t* comp_order, const int32_t* rel_slot,
@@ -131,6 +132,7 @@ int renet_set_gemm_engine(int engine) { return set_gemm_mode(engine); }
 int renet_get_gemm_engine(void) { return gemm_mode(); }
 int renet_set_gather_variant(int variant) { return set_gather_variant(variant); }
 int renet_set_weight_generation(int64_t generation) { renet::set_weight_generation(generation); return RENET_OK; }
+int renet_set_hot_relations(const int32_t* hot_rel, int32_t n_hot, int32_t R2) { return set_hot_relations(hot_rel, n_hot, R2); }
 int renet_set_scratch(void* device_ptr, int64_t bytes) {
   RENET_CHECK_ARG(bytes >= 0 && (device_ptr != nullptr || bytes == 0), "renet_set_scratch: bad arguments");
   set_scratch(device_ptr, bytes);
@@ -201,7 +203,7 @@ int renet_rgcn_gather(const float* H, const int32_t* h_index, const float* W, co
   if (rc) return rc;
   RENET_CHECK_ARG(E == 0 || (col_src && col_type), "renet_rgcn_gather: null edge arrays");
   return launch_rgcn_gather(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, N, E, d_in, d_out, num_bases,
-                            relu, has_loop, (cudaStream_t)stream);
+                            relu, has_loop, (cudaStream_t)stream, R2);
 }
 
 int renet_rgcn_gather_comp(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
@@ -238,7 +240,7 @@ int renet_rgcn_block_fwd(const float* H, const int32_t* h_index, const float* W,
     if (rc) return rc;
   }
   return launch_rgcn_gather(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, N, E, d_in, d_out, num_bases,
-                            relu, Wloop != nullptr, (cudaStream_t)stream);
+                            relu, Wloop != nullptr, (cudaStream_t)stream, R2);
 }
 
 int renet_rgcn_block_bwd(const float* H, const int32_t* h_index, const float* W, const float* Wloop,

@@ -16,6 +16,9 @@
 #include "rgcn_tile.cuh"
 #include "rgcn_comp.cuh"
 #include "rgcn_ring.cuh"
+#include "rgcn_hot.cuh"
+#include <mutex>
+#include <vector>
 
 namespace renet {
 namespace {
@@ -305,10 +308,59 @@ int set_gather_variant(int v) {
   return prev;
 }
 
+// ---- hot relations (renet_set_hot_relations): a performance hint for the persistent gather (rgcn_hot.cuh) ------------
+namespace {
+struct HotSet { int device; int R2; int n_hot; int32_t* rel_slot; int32_t* hot_rel; };
+std::mutex g_hot_mu;
+std::vector<int32_t> g_hot_host;     // the hint as given; uploaded lazily per device
+int g_hot_R2 = 0;
+std::vector<HotSet> g_hot_dev;
+
+// device copy of the hint for the current device, or nullptr
+const HotSet* hot_set_for_device(int R2) {
+  std::lock_guard<std::mutex> lk(g_hot_mu);
+  if (g_hot_host.empty() || R2 != g_hot_R2) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  for (const auto& h : g_hot_dev) if (h.device == dev) return &h;
+  HotSet h{dev, g_hot_R2, (int)g_hot_host.size(), nullptr, nullptr};
+  std::vector<int32_t> slot(g_hot_R2, -1);
+  for (int i = 0; i < h.n_hot; ++i) slot[g_hot_host[i]] = i;
+  if (cudaMalloc(&h.rel_slot, sizeof(int32_t) * g_hot_R2) != cudaSuccess ||
+      cudaMalloc(&h.hot_rel, sizeof(int32_t) * h.n_hot) != cudaSuccess ||
+      cudaMemcpy(h.rel_slot, slot.data(), sizeof(int32_t) * g_hot_R2, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(h.hot_rel, g_hot_host.data(), sizeof(int32_t) * h.n_hot, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  g_hot_dev.push_back(h);
+  return &g_hot_dev.back();
+}
+}  // namespace
+
+int set_hot_relations(const int32_t* hot_rel_host, int n_hot, int R2) {
+  std::lock_guard<std::mutex> lk(g_hot_mu);
+  for (auto& h : g_hot_dev) { cudaFree(h.rel_slot); cudaFree(h.hot_rel); }
+  g_hot_dev.clear();
+  g_hot_host.clear();
+  g_hot_R2 = 0;
+  if (n_hot <= 0 || hot_rel_host == nullptr) return RENET_OK;        // hint cleared
+  if (n_hot > kHotMax || R2 <= 0) { set_error("renet_set_hot_relations: n_hot must be in [0,%d], R2 > 0", kHotMax); return RENET_ERR_INVALID_ARG; }
+  std::vector<char> seen(R2, 0);
+  for (int i = 0; i < n_hot; ++i) {
+    const int32_t r = hot_rel_host[i];
+    if (r < 0 || r >= R2 || seen[r]) { set_error("renet_set_hot_relations: entries must be distinct ids in [0,%d)", R2); return RENET_ERR_INVALID_ARG; }
+    seen[r] = 1;
+  }
+  g_hot_host.assign(hot_rel_host, hot_rel_host + n_hot);
+  g_hot_R2 = R2;
+  return RENET_OK;
+}
+
 int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
                        const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout,
                        int64_t N, int64_t E, int d_in, int d_out, int nb, int relu, int has_loop,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, int R2) {
   if (N == 0) return RENET_OK;
   const int passthrough = (E == 0) ? 1 : 0;
   const bool fast = d_in == 200 && d_out == 200 && nb == 100 &&
@@ -320,6 +372,36 @@ int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, c
     const unsigned n_tiles = (unsigned)((N + kTileNodes - 1) / kTileNodes);
     const unsigned grid = variant == 2 ? min(n_tiles, (unsigned)(kNumSMs * 3)) : n_tiles;
     const int32_t* order = nullptr;   // optional heaviest-first tile order: measured, no gain
+    // experimental (variant 7 + renet_set_hot_relations): persistent kernel with the hot relation rows in shared
+    // memory; bit-identical, measured slower than the tile kernel (61 vs 52 us), see DESIGN.md section 5
+    const HotSet* hot = (!passthrough && variant == 7) ? hot_set_for_device(R2) : nullptr;
+    if (hot != nullptr) {
+      static bool attr_done[8] = {false, false, false, false, false, false, false, false};
+      const int hkey = (relu ? 4 : 0) | (has_loop ? 2 : 0) | (h_index ? 1 : 0);
+      const unsigned hgrid = min((n_tiles + kHotGroups - 1) / kHotGroups, (unsigned)kNumSMs);
+      const unsigned hblock = kHotGroups * kTileWarps * 32;
+#define RENET_LAUNCH_HOT(R, L, I)                                                                               \
+  do {                                                                                                          \
+    if (!attr_done[hkey]) {                                                                                     \
+      RENET_CHECK_CUDA(cudaFuncSetAttribute(rgcn_gather_hot_kernel<R, L, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHotSmemBytes)); \
+      attr_done[hkey] = true;                                                                                   \
+    }                                                                                                           \
+    rgcn_gather_hot_kernel<R, L, I><<<hgrid, hblock, kHotSmemBytes, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, hot->rel_slot, hot->hot_rel, hot->n_hot); \
+  } while (0)
+      switch (hkey) {
+        case 0: RENET_LAUNCH_HOT(false, false, false); break;
+        case 1: RENET_LAUNCH_HOT(false, false, true); break;
+        case 2: RENET_LAUNCH_HOT(false, true, false); break;
+        case 3: RENET_LAUNCH_HOT(false, true, true); break;
+        case 4: RENET_LAUNCH_HOT(true, false, false); break;
+        case 5: RENET_LAUNCH_HOT(true, false, true); break;
+        case 6: RENET_LAUNCH_HOT(true, true, false); break;
+        default: RENET_LAUNCH_HOT(true, true, true); break;
+      }
+#undef RENET_LAUNCH_HOT
+      RENET_CHECK_LAUNCH("rgcn_gather_hot_kernel");
+      return RENET_OK;
+    }
 #define RENET_LAUNCH_GATHER(R, L, I)                                                                            \
   if (variant == 6)                                                                                             \
     rgcn_gather_ring_kernel<R, L, I><<<n_tiles, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N); \

@@ -76,3 +76,15 @@ for layer1 in (True, False):
         run('tile', v, layer1)
         got = check(v, layer1)
         print('      max |variant %d - variant %d| = %.3e (ref max %.3e)' % (v, variants[0], max(float((a - b).abs().max()) for a, b in zip(got, ref)), float(ref[0].abs().max())))
+    # persistent kernel with the hot relation rows in shared memory (renet_set_hot_relations)
+    for pairs in (24, 16):
+        R = 256
+        cnt = np.bincount(gs.type_s % R, minlength=R)
+        top = np.argsort(-cnt, kind='stable')[:pairs]
+        hot = np.ascontiguousarray(np.concatenate((top, top + R)).astype(np.int32))
+        _lib.check(L.renet_set_hot_relations(hot.ctypes.data_as(_lib.ctypes.c_void_p), len(hot), 2 * R), 'hot')
+        print('hot set: %d rows, edge share %.3f' % (len(hot), cnt[top].sum() / cnt.sum()))
+        run('hot', 7, layer1)
+        got = check(7, layer1)
+        print('      max |hot - variant %d| = %.3e' % (variants[0], max(float((a - b).abs().max()) for a, b in zip(got, ref))))
+        L.renet_set_hot_relations(None, 0, 0)
