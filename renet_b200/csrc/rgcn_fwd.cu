@@ -26,7 +26,7 @@ namespace {
 // VARIANT 0: one tile per CTA, source rows streamed past L1.  1: source rows allocate in L1.  2: persistent
 // CTAs, each walking a contiguous range of tiles (same component -> source rows re-used from L1).
 template <bool RELU, bool HAS_LOOP, bool INDEXED, int NODES = kTileNodes, int VARIANT = 0>
-__global__ void __launch_bounds__(kTileWarps * 32, 3)
+__global__ void __launch_bounds__(kTileWarps * 32, 768 / (kTileWarps * 32))
 rgcn_gather_d200_kernel(const float* __restrict__ H, const int32_t* __restrict__ h_index,
                         const float* __restrict__ W, const int32_t* __restrict__ row_ptr,
                         const int32_t* __restrict__ col_src, const int32_t* __restrict__ col_type,
