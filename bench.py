@@ -27,6 +27,13 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 for every rank unless the application tunes it ("please further tune the variable
+# for optimal performance in your application as needed").  Measured on a 2-GPU box: with 1 the end-to-end loop ran at
+# 6.75 ms/step per rank, with 8 at 1.52 ms/step; the kernels' own numbers do not depend on it.  Must happen before numpy /
+# torch load their OpenMP runtime.
+if os.environ.get('OMP_NUM_THREADS') == '1' and 'LOCAL_RANK' in os.environ:
+    os.environ['OMP_NUM_THREADS'] = '8'
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -56,6 +63,15 @@ def algorithmic_bytes(N, E, R2):
     """SURVEY.md section 8(d), fp32 features, int32 indices, per fused-gather launch:
     E*(4h + 12) + N*(4h loop read + 4h write + 4 norm) + R2*(h*h/nb)*4."""
     return E * (4 * H_DIM + 12) + N * (8 * H_DIM + 4) + R2 * (H_DIM * H_DIM // NUM_BASES) * 4
+
+
+def _cpu_quota():
+    """CPUs the container may actually use (cgroup v2 cpu.max), or None: `cores` threads are started, the quota caps them."""
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        return None if q == 'max' else round(float(q) / float(per), 2)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -143,7 +159,9 @@ def cpu_reference_sample(tkg, torch, steps, warmup):
     batch (a bounded sample of the GPU arm's step, which is two directions)."""
     from oracle import restate
     from renet_b200 import utils
-    torch.set_num_threads(os.cpu_count() or 1)
+    q = _cpu_quota()
+    # all the host threads the container can actually run: more threads than the cgroup quota only thrash
+    torch.set_num_threads(max(1, min(os.cpu_count() or 1, int(q + 0.5))) if q else (os.cpu_count() or 1))
     q, sh, oh = tkg.batch(0, BATCH, tail_only=False)
     hb = utils.assemble_history_batch_host(sh[0], sh[1], q[:, 0], tkg.graph_dict)
     g = hb.graph
@@ -172,7 +190,7 @@ def cpu_reference_sample(tkg, torch, steps, warmup):
             step()
             times.append(time.perf_counter() - t0)
     med = float(np.median(times))
-    return {'value': 2 * E / med, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+    return {'value': 2 * E / med, 'unit': UNIT, 'cores': torch.get_num_threads(), 'host_cpu_quota': _cpu_quota(), 'kind': 'port',
             'sample': 'one direction x 2 layers of one batch (N=%d, E=%d), reference op sequence '
                       '(index_select+bmm+index_add) in torch CPU fp32, median of %d' % (N, E, steps),
             'ms_per_step': med * 1e3, 'edge_msgs_per_step': 2 * E}
@@ -192,7 +210,7 @@ def run_reference(args):
             'steps': steps, 'warmup': 1, 'ms_per_step': res['ms_per_step'], 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'sample': res['sample']},
-            'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+            'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'host_cpu_quota', 'kind', 'sample')},
             'e2e': {'value': res['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
@@ -410,7 +428,11 @@ def run_ours(args):
             msgs = sum(2 * g.E for g in graphs)
             return h2d, d2h, msgs, dt
 
-        E2E_DEPTH, E2E_WORKERS = 4, 8
+        # loader threads per rank: 8 when the host has room; under a cgroup CPU quota leave a core per rank for the
+        # consumer thread (a plan takes ~0.6 ms of one core, a step needs two: 2 threads keep up with a 1.3 ms step)
+        quota = _cpu_quota()
+        E2E_DEPTH = 4
+        E2E_WORKERS = 8 if not quota else max(2, min(8, int(quota / max(world, 1)) - 2))
         k_e2e = max(4, args.steps)
         h2d, d2h, msgs, dt = run_e2e(max(3, args.warmup), k_e2e, 0)
         tt = torch.tensor([dt, float(msgs)], device=dev, dtype=torch.float64)
@@ -431,7 +453,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_sample(tkg, torch, 3, 1)
-        cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+        cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'host_cpu_quota', 'kind', 'sample')}
 
     if rank == 0:
         g0 = pool[0]['dirs']

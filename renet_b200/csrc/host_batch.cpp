@@ -50,17 +50,18 @@ extern "C" int renet_set_host_threads(int n) {
 namespace {
 // Steps 1-3 of the batching, shared by the all-host batcher and the host half of the device batcher.
 struct Plan {
-  std::vector<int32_t> len, comp_graph, row_comp, row_srow, row_seq, newid;
+  std::vector<int32_t> len, comp_graph, row_comp, row_srow, row_seq, newid, node_ent;
   std::vector<int64_t> mark_off, comp_start;
   int max_len = 0;
   int64_t Q = 0, S = 0, G = 0, N = 0;
+  int32_t* nid = nullptr;       // where the node marks / ids live: newid, or the caller's output buffer
 };
 
 // returns RENET_OK / error; S == 0 leaves the plan empty
-int build_plan(Plan& P, const char* fn, int64_t T, const int64_t* g_node_off, const int64_t* h_samp_off,
+int build_plan(Plan& P, const char* fn, int64_t T, const int64_t* g_node_off, const int32_t* g_node_ent, const int64_t* h_samp_off,
                const int64_t* h_samp_entry, const int32_t* h_ent_graph, const int32_t* h_ent_srow, const int64_t* h_ent_off,
                const int32_t* h_nbr_row, const int64_t* sample_idx, int64_t B, int32_t sort, int64_t* s_idx_out,
-               int32_t max_len_capacity) {
+               int32_t max_len_capacity, int32_t* newid_out = nullptr, int64_t newid_capacity = 0) {
   // ---- 1. order samples by history length, descending, stable (model.py:80-81, utils.py:212-215) ----
   P.len.resize(B);
   int max_len = 0;
@@ -91,37 +92,78 @@ int build_plan(Plan& P, const char* fn, int64_t T, const int64_t* g_node_off, co
   P.row_comp.resize(S); P.row_srow.resize(S); P.row_seq.resize(S);
   std::vector<int64_t> row_entry(S);
   int64_t r = 0;
-  for (int64_t q = 0; q < Q; ++q) {
+  for (int64_t q = 0; q < Q; ++q) {           // pass A: the samples' entry lists (contiguous per sample)
     const int64_t smp = sample_idx[s_idx_out[q]];
+    if (q + 4 < Q) __builtin_prefetch(h_samp_entry + h_samp_off[sample_idx[s_idx_out[q + 4]]]);
     for (int64_t ei = h_samp_off[smp]; ei < h_samp_off[smp + 1]; ++ei, ++r) {
-      const int64_t e = h_samp_entry[ei];
-      const int32_t g = h_ent_graph[e];
-      if (comp_of_graph[g] < 0) { comp_of_graph[g] = (int32_t)P.comp_graph.size(); P.comp_graph.push_back(g); }
-      P.row_comp[r] = comp_of_graph[g];
-      P.row_srow[r] = h_ent_srow[e];
+      row_entry[r] = h_samp_entry[ei];
       P.row_seq[r] = (int32_t)q;
-      row_entry[r] = e;
     }
+  }
+  constexpr int64_t kAheadB = 16;
+  for (int64_t i = 0; i < S; ++i) {           // pass B: per-entry fields (random reads: prefetched ahead)
+    if (i + kAheadB < S) {
+      __builtin_prefetch(h_ent_graph + row_entry[i + kAheadB]);
+      __builtin_prefetch(h_ent_srow + row_entry[i + kAheadB]);
+    }
+    const int64_t e = row_entry[i];
+    const int32_t g = h_ent_graph[e];
+    if (comp_of_graph[g] < 0) { comp_of_graph[g] = (int32_t)P.comp_graph.size(); P.comp_graph.push_back(g); }
+    P.row_comp[i] = comp_of_graph[g];
+    P.row_srow[i] = h_ent_srow[e];
   }
   const int64_t G = P.G = (int64_t)P.comp_graph.size();
   // ---- 3. node sets: mark local rows of every component's graph, then number them ----------------------------
   P.mark_off.assign(G + 1, 0);
   for (int64_t c = 0; c < G; ++c) P.mark_off[c + 1] = P.mark_off[c] + (g_node_off[P.comp_graph[c] + 1] - g_node_off[P.comp_graph[c]]);
-  P.newid.assign(P.mark_off[G], -1);       // -1 = not selected; later the batched node id
+  // marks go into a bitmap (M bits: 25 KB for ICEWS18, L1-resident) -- the marking loop is a chain of dependent random
+  // reads into the history store, so the entries a few rows ahead are prefetched -- and numbering walks the set bits
+  // only: in global bit order = (component, local row) order, which is the batched node order.
+  const int64_t M = P.mark_off[G];
+  std::vector<uint64_t> bits((M + 63) / 64 + 1, 0);
+  constexpr int64_t kAhead = 12;
   for (int64_t i = 0; i < S; ++i) {
-    int32_t* m = P.newid.data() + P.mark_off[P.row_comp[i]];
-    m[P.row_srow[i]] = 0;
+    if (i + kAhead < S) {
+      const int64_t ea = row_entry[i + kAhead];
+      __builtin_prefetch(h_ent_off + ea);
+      if (i + kAhead / 2 < S) __builtin_prefetch(h_nbr_row + h_ent_off[row_entry[i + kAhead / 2]]);
+    }
+    const int64_t base = P.mark_off[P.row_comp[i]];
+    int64_t b = base + P.row_srow[i];
+    bits[b >> 6] |= uint64_t(1) << (b & 63);
     const int64_t e = row_entry[i];
-    for (int64_t k = h_ent_off[e]; k < h_ent_off[e + 1]; ++k) m[h_nbr_row[k]] = 0;
+    for (int64_t k = h_ent_off[e]; k < h_ent_off[e + 1]; ++k) {
+      b = base + h_nbr_row[k];
+      bits[b >> 6] |= uint64_t(1) << (b & 63);
+    }
   }
-  int64_t N = 0;
+  if (newid_out != nullptr && M <= newid_capacity) {      // build the ids in place in the caller's buffer
+    P.nid = newid_out;
+    memset(P.nid, 0xff, (size_t)M * 4);
+  } else {
+    P.newid.assign(M, -1);       // -1 = not selected; else the batched node id
+    P.nid = P.newid.data();
+  }
   P.comp_start.assign(G + 1, 0);
-  for (int64_t c = 0; c < G; ++c) {
-    P.comp_start[c] = N;
-    int32_t* m = P.newid.data() + P.mark_off[c];
-    const int64_t n = P.mark_off[c + 1] - P.mark_off[c];
-    for (int64_t j = 0; j < n; ++j) if (m[j] == 0) m[j] = (int32_t)N++;
+  P.node_ent.clear();
+  P.node_ent.reserve(S * 4);
+  int64_t N = 0, c = 0;
+  const int32_t* ent = G > 0 ? g_node_ent + g_node_off[P.comp_graph[0]] : nullptr;
+  for (int64_t w = 0; w < (int64_t)bits.size(); ++w) {
+    uint64_t x = bits[w];
+    while (x) {
+      const int64_t gidx = (w << 6) + __builtin_ctzll(x);
+      x &= x - 1;
+      while (gidx >= P.mark_off[c + 1]) {        // entered the next component (also skips components without marks)
+        ++c;
+        P.comp_start[c] = N;
+        ent = g_node_ent + g_node_off[P.comp_graph[c]];
+      }
+      P.nid[gidx] = (int32_t)N++;
+      P.node_ent.push_back(ent[gidx - P.mark_off[c]]);
+    }
   }
+  while (c < G) P.comp_start[++c] = N;
   P.comp_start[G] = N;
   P.N = N;
   return RENET_OK;
@@ -131,7 +173,7 @@ int build_plan(Plan& P, const char* fn, int64_t T, const int64_t* g_node_off, co
 void emit_sequences(const Plan& P, const int64_t* s_idx_out, int32_t* o_readout, int32_t* o_rowcomp, int32_t* o_rowseq,
                     int32_t* o_seqstart, int32_t* o_seqlen, int32_t* o_packed, int32_t* batch_sizes_out) {
   for (int64_t i = 0; i < P.S; ++i) {
-    o_readout[i] = P.newid[P.mark_off[P.row_comp[i]] + P.row_srow[i]];
+    o_readout[i] = P.nid[P.mark_off[P.row_comp[i]] + P.row_srow[i]];
     o_rowcomp[i] = P.row_comp[i];
     o_rowseq[i] = P.row_seq[i];
   }
@@ -165,7 +207,7 @@ extern "C" int renet_host_assemble_batch(
     int64_t* sizes /* [10]: N, E, S, Q, G, max_len, words_used, n_hot_s, n_hot_o, 0 */) {
   if (B < 0 || !sizes || R2 < 0 || n_hot_max < 0) { renet::set_error("renet_host_assemble_batch: bad arguments"); return RENET_ERR_INVALID_ARG; }
   Plan P;
-  int prc = build_plan(P, "renet_host_assemble_batch", T, g_node_off, h_samp_off, h_samp_entry, h_ent_graph, h_ent_srow,
+  int prc = build_plan(P, "renet_host_assemble_batch", T, g_node_off, g_node_ent, h_samp_off, h_samp_entry, h_ent_graph, h_ent_srow,
                        h_ent_off, h_nbr_row, sample_idx, B, sort, s_idx_out, max_len_capacity);
   if (prc != RENET_OK) return prc;
   const int64_t Q = P.Q, S = P.S, G = P.G, N = P.N;
@@ -173,14 +215,14 @@ extern "C" int renet_host_assemble_batch(
   sizes[2] = S; sizes[3] = Q; sizes[5] = max_len;
   if (S == 0) { sizes[0] = sizes[1] = sizes[4] = sizes[6] = 0; return RENET_OK; }
   const std::vector<int32_t>& comp_graph = P.comp_graph;
-  const std::vector<int32_t>& newid = P.newid;
+  const int32_t* newid = P.nid;
   const std::vector<int64_t>& mark_off = P.mark_off;
   const std::vector<int64_t>& comp_start = P.comp_start;
   // ---- 4. count induced edges per component (utils.make_subgraph, utils.py:115-131), in parallel -------------
   std::vector<int64_t> comp_estart(G + 1, 0);
   parallel_for(G, [&](int64_t c) {
     const int32_t g = comp_graph[c];
-    const int32_t* m = newid.data() + mark_off[c];
+    const int32_t* m = newid + mark_off[c];
     int64_t cnt = 0;
     for (int64_t k = g_edge_off[g]; k < g_edge_off[g + 1]; ++k) cnt += (m[g_src[k]] >= 0) & (m[g_dst[k]] >= 0);
     comp_estart[c + 1] = cnt;
@@ -209,12 +251,10 @@ extern "C" int renet_host_assemble_batch(
   int32_t* o_packed = o_seqlen + Q;
   // ---- 5. emit nodes + edges (per-timestamp edge lists are destination-sorted => CSR for free) ----------------
   o_rp[0] = 0;
+  memcpy(o_node, P.node_ent.data(), (size_t)N * 4);
   parallel_for(G, [&](int64_t c) {
     const int32_t g = comp_graph[c];
-    const int32_t* m = newid.data() + mark_off[c];
-    const int32_t* ent = g_node_ent + g_node_off[g];
-    const int64_t n = mark_off[c + 1] - mark_off[c];
-    for (int64_t j = 0; j < n; ++j) if (m[j] >= 0) o_node[m[j]] = ent[j];
+    const int32_t* m = newid + mark_off[c];
     int64_t ecur = comp_estart[c];
     int64_t node = comp_start[c];            // next node whose row_ptr end is not yet written
     for (int64_t k = g_edge_off[g]; k < g_edge_off[g + 1]; ++k) {
@@ -285,8 +325,8 @@ extern "C" int renet_host_plan_batch(
     int64_t* sizes /* [10]: N, E_cand, S, Q, G, max_len, words_used, M, 0, 0 */) {
   if (B < 0 || !sizes) { renet::set_error("renet_host_plan_batch: bad arguments"); return RENET_ERR_INVALID_ARG; }
   Plan P;
-  int prc = build_plan(P, "renet_host_plan_batch", T, g_node_off, h_samp_off, h_samp_entry, h_ent_graph, h_ent_srow, h_ent_off,
-                       h_nbr_row, sample_idx, B, sort, s_idx_out, max_len_capacity);
+  int prc = build_plan(P, "renet_host_plan_batch", T, g_node_off, g_node_ent, h_samp_off, h_samp_entry, h_ent_graph, h_ent_srow, h_ent_off,
+                       h_nbr_row, sample_idx, B, sort, s_idx_out, max_len_capacity, out, out_capacity);
   if (prc != RENET_OK) return prc;
   const int64_t Q = P.Q, S = P.S, G = P.G, N = P.N;
   for (int i = 0; i < 10; ++i) sizes[i] = 0;
@@ -311,13 +351,8 @@ extern "C" int renet_host_plan_batch(
   int32_t* o_cg = o_sidx + B;
   int32_t* o_moff = o_cg + G;
   int32_t* o_coff = o_moff + G + 1;
-  memcpy(o_newid, P.newid.data(), (size_t)M * 4);
-  for (int64_t c = 0; c < G; ++c) {
-    const int32_t* m = P.newid.data() + P.mark_off[c];
-    const int32_t* ent = g_node_ent + g_node_off[P.comp_graph[c]];
-    const int64_t n = P.mark_off[c + 1] - P.mark_off[c];
-    for (int64_t j = 0; j < n; ++j) if (m[j] >= 0) o_node[m[j]] = ent[j];
-  }
+  if (P.nid != o_newid) memcpy(o_newid, P.nid, (size_t)M * 4);
+  memcpy(o_node, P.node_ent.data(), (size_t)N * 4);
   emit_sequences(P, s_idx_out, o_readout, o_rowcomp, o_rowseq, o_seqstart, o_seqlen, o_packed, batch_sizes_out);
   for (int64_t i = 0; i < B; ++i) o_sidx[i] = (int32_t)s_idx_out[i];
   int64_t acc = 0;
