@@ -46,8 +46,8 @@ int64_t renet_launch_count(void);
  * renet_set_gemm_engine returns the previous engine. */
 int renet_set_gemm_engine(int engine);
 int renet_get_gemm_engine(void);
-/* Tuning knob for renet_rgcn_gather's d=200 kernel (tile size / occupancy variants, see rgcn_fwd.cu);
- * results are identical across variants.  Returns the previous value. */
+/* Experiment knob for renet_rgcn_gather's d=200 forward kernel (0 = default; 1, 2, 6, 7 = measured alternatives, see
+ * rgcn_fwd.cu); results agree across variants (0, 6, 7 bit for bit).  Returns the previous value. */
 int renet_set_gather_variant(int variant);
 /* Packed-weight cache of the tcgen05 GEMM engine.  The engine consumes weights (self-loop matrices, GRU W_ih / W_hh)
  * in a packed shared-memory operand image; packing is a kernel launch per weight per call.  Declaring a weight

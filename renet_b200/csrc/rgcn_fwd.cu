@@ -86,121 +86,6 @@ rgcn_gather_d200_kernel(const float* __restrict__ H, const int32_t* __restrict__
   }
 }
 
-// Feature-split version: blockIdx.y selects one half (100 of the 200 features = 50 blocks) of the tile's rows.
-// Per edge a lane then holds 2 x (float2 + float4) instead of 4 x, so the two-edges-in-flight loop needs ~50
-// registers instead of 80 and 5 CTAs (40 warps) fit per SM instead of 3 (24): more loads in flight per SM for
-// the same latency.  Index loads are duplicated between the two halves; feature / weight bytes are not.
-template <bool RELU, bool HAS_LOOP, bool INDEXED, int U, int MINB>
-__global__ void __launch_bounds__(kTileWarps * 32, MINB)
-rgcn_gather_half_kernel(const float* __restrict__ H, const int32_t* __restrict__ h_index,
-                        const float* __restrict__ W, const int32_t* __restrict__ row_ptr,
-                        const int32_t* __restrict__ col_src, const int32_t* __restrict__ col_type,
-                        const float* __restrict__ norm, float* __restrict__ Hout, int N) {
-  __shared__ __align__(16) float agg[kTileNodes][100];
-  __shared__ __align__(16) float loopbuf[HAS_LOOP ? kTileNodes : 1][100];
-  __shared__ float normbuf[kTileNodes];
-  __shared__ int s_rp[kTileNodes + 1];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int half = blockIdx.y;
-  const int v0 = blockIdx.x * kTileNodes;
-  const int nv = min(kTileNodes, N - v0);
-  if (HAS_LOOP)
-    for (int i = tid; i < nv * 25; i += kTileWarps * 32) {
-      const int r = i / 25, c = (i % 25) * 4;
-      cp_async16(&loopbuf[r][c], Hout + (int64_t)(v0 + r) * 200 + half * 100 + c);
-    }
-  cp_async_commit();
-  if (tid < nv) normbuf[tid] = __ldg(norm + v0 + tid);
-  for (int i = tid; i < kTileNodes * 100; i += kTileWarps * 32) (&agg[0][0])[i] = 0.f;
-  if (tid <= nv) s_rp[tid] = __ldg(row_ptr + v0 + tid);
-  __syncthreads();
-  {
-    const bool active = lane < 25;
-    const int ebeg = s_rp[0], eend = s_rp[nv];
-    const int chunk = (eend - ebeg + kTileWarps - 1) / kTileWarps;
-    const int e0 = ebeg + warp * chunk;
-    const int e1 = min(eend, e0 + chunk);
-    if (e0 < e1) {
-      int node = 0;
-      while (s_rp[node + 1] <= e0) ++node;
-      int node_end = s_rp[node + 1];
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      auto flush = [&](int nd) {
-        if (active) {
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            atomicAdd(&agg[nd][2 * (lane + 25 * k)], acc[2 * k]);
-            atomicAdd(&agg[nd][2 * (lane + 25 * k) + 1], acc[2 * k + 1]);
-            acc[2 * k] = acc[2 * k + 1] = 0.f;
-          }
-        }
-      };
-      auto advance = [&](int e) {
-        if (e >= node_end) {
-          flush(node);
-          do { ++node; node_end = s_rp[node + 1]; } while (e >= node_end);
-        }
-      };
-      const float* Xh = H + half * 100 + 2 * lane;
-      const float* Wh = W + half * 200 + 4 * lane;
-      for (int base = e0; base < e1; base += 32) {
-        const int e = base + lane;
-        int my_s = 0, my_t = 0;
-        if (e < e1) {
-          my_s = __ldg(col_src + e);
-          my_t = __ldg(col_type + e);
-          if (INDEXED) my_s = __ldg(h_index + my_s);
-        }
-        const int cnt = min(32, e1 - base);
-        for (int j = 0; j < cnt; j += U) {        // U edges (4U loads) in flight per lane
-          float2 hx[U][2];
-          float4 wx[U][2];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int ju = min(j + u, cnt - 1);
-            const int su = __shfl_sync(0xffffffffu, my_s, ju), tu = __shfl_sync(0xffffffffu, my_t, ju);
-            if (active) {
-              const float* xp = Xh + (int64_t)su * 200;
-              const float* wp = Wh + (int64_t)tu * 400;
-              hx[u][0] = ldg_f2_stream(xp); hx[u][1] = ldg_f2_stream(xp + 50);
-              wx[u][0] = ldg_f4(wp); wx[u][1] = ldg_f4(wp + 100);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if (j + u < cnt) {
-              advance(base + j + u);
-              if (active) {
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                  const float4 w = wx[u][k];
-                  acc[2 * k] = fmaf(hx[u][k].x, w.x, fmaf(hx[u][k].y, w.z, acc[2 * k]));
-                  acc[2 * k + 1] = fmaf(hx[u][k].x, w.y, fmaf(hx[u][k].y, w.w, acc[2 * k + 1]));
-                }
-              }
-            }
-          }
-        }
-      }
-      flush(node);
-    }
-  }
-  cp_async_wait_all();
-  __syncthreads();
-  for (int i = tid; i < nv * 50; i += kTileWarps * 32) {
-    const int r = i / 50, c = (i % 50) * 2;
-    const float2 a = *reinterpret_cast<const float2*>(&agg[r][c]);
-    const float nvv = normbuf[r];
-    float2 o = make_float2(a.x * nvv, a.y * nvv);
-    if (HAS_LOOP) {
-      const float2 l = *reinterpret_cast<const float2*>(&loopbuf[r][c]);
-      o.x += l.x; o.y += l.y;
-    }
-    if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
-    *reinterpret_cast<float2*>(Hout + (int64_t)(v0 + r) * 200 + half * 100 + c) = o;
-  }
-}
-
 // Component-resident version (rgcn_comp.cuh): one CTA per component, features and hot relation rows staged
 // in shared memory once, two 8-warp groups walking 16-destination tiles.
 template <bool RELU, bool HAS_LOOP, bool INDEXED>
@@ -292,8 +177,12 @@ __global__ void rgcn_gather_generic_kernel(const float* __restrict__ H, const in
 
 }  // namespace
 
-// experiment knob (RENET_GATHER_VARIANT / renet_set_gather_variant): 0 = at least 3 CTAs/SM (default),
-// 1 = at least 4 CTAs/SM (64 registers)
+// experiment knob (RENET_GATHER_VARIANT / renet_set_gather_variant) for the d=200 forward gather:
+//   0 default tile kernel (deterministic hand-over, source rows streamed past L1)
+//   1 source rows allocate in L1, shared-memory atomics     2 persistent CTAs over contiguous tile ranges
+//   6 per-warp cp.async ring of source rows (rgcn_ring.cuh) 7 persistent CTAs with the hot relation rows in shared
+//     memory (rgcn_hot.cuh, needs renet_set_hot_relations)
+// All measured slower than 0; 0, 6 and 7 are bit-identical.
 static int g_gather_variant = -1;
 int gather_variant() {
   if (g_gather_variant < 0) {
@@ -405,12 +294,6 @@ int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, c
 #define RENET_LAUNCH_GATHER(R, L, I)                                                                            \
   if (variant == 6)                                                                                             \
     rgcn_gather_ring_kernel<R, L, I><<<n_tiles, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N); \
-  else if (variant == 3)                                                                                             \
-    rgcn_gather_half_kernel<R, L, I, 4, 4><<<dim3(n_tiles, 2), block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N); \
-  else if (variant == 4)                                                                                        \
-    rgcn_gather_half_kernel<R, L, I, 2, 6><<<dim3(n_tiles, 2), block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N); \
-  else if (variant == 5)                                                                                        \
-    rgcn_gather_half_kernel<R, L, I, 3, 5><<<dim3(n_tiles, 2), block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N); \
   else if (variant == 1)                                                                                        \
     rgcn_gather_d200_kernel<R, L, I, kTileNodes, 1><<<grid, block, 0, stream>>>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, passthrough, nullptr); \
   else if (variant == 2)                                                                                        \

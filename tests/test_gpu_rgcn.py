@@ -229,8 +229,17 @@ def test_component_resident_kernel_vs_oracle(G):
                                       N, len(src), len(sizes), 200, 200, 100, R2, 1, 1, _lib.stream())
         _lib.check(rc, 'renet_rgcn_gather_comp')
         assert rel_err(out.cpu().numpy(), ref.numpy()) < TOL, (use_hot, use_order)
-    # every tile-kernel variant gives the same result
-    for variant in (1, 2, 3, 4, 5, 0):
-        L.renet_set_gather_variant(variant)
-        tile = G.layer_fwd(entd, idx, Wd, Wld, rp, cs, ct, nrm, N, len(src), 200, 200, 100, True)
-        assert rel_err(tile.cpu().numpy(), ref.numpy()) < TOL, variant
+    # every forward variant gives the same result; the ring (6) and hot-relation (7) kernels keep the default kernel's
+    # summation order and are bit-identical to it
+    hot = np.ascontiguousarray(np.argsort(-np.bincount(et, minlength=R2), kind='stable')[:40].astype(np.int32))
+    _lib.check(L.renet_set_hot_relations(hot.ctypes.data_as(_lib.ctypes.c_void_p), len(hot), R2), 'hot')
+    try:
+        for variant in (1, 2, 6, 7, 0):
+            L.renet_set_gather_variant(variant)
+            other = G.layer_fwd(entd, idx, Wd, Wld, rp, cs, ct, nrm, N, len(src), 200, 200, 100, True)
+            assert rel_err(other.cpu().numpy(), ref.numpy()) < TOL, variant
+            if variant in (6, 7, 0):
+                assert torch.equal(other, tile), variant
+    finally:
+        L.renet_set_gather_variant(0)
+        L.renet_set_hot_relations(None, 0, 0)
