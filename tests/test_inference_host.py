@@ -54,3 +54,25 @@ def test_eval_flow_matches_reference_golden_with_oracle_encode():
     ctx['model'].aggregator.encode = _oracle_encode(ctx)
     res = eval_flow(ctx, 'cpu')
     check_eval_against_golden(res, ctx['ev'])
+
+
+def test_rebinding_switch_scores_the_triple_itself():
+    """RENet.reference_rebinding = False: the first triple after a timestamp change is scored with its own (s, o), i.e.
+    exactly like a repeated call (the reference's numbers for that triple come from model.py:279,290 re-binding s / o)."""
+    ctx = eval_setup('cpu')
+    m, quads, gm = ctx['model'], ctx['quads'], ctx['gm']
+    m.aggregator.encode = _oracle_encode(ctx)
+    m.reference_rebinding = False
+    S, ST, O, OT = ctx['hist']
+    i = int(ctx['ev']['rolled_at'])
+    m.latest_time = torch.tensor(ctx['t_test'])
+    torch.manual_seed(1234)
+    trip = torch.from_numpy(quads[i])
+    with torch.no_grad():
+        l1, sp1, op1 = m.predict(trip, (S[i], ST[i]), (O[i], OT[i]), gm)      # rolls over, then scores (s, o) itself
+        l2, sp2, op2 = m.predict(trip, (S[i], ST[i]), (O[i], OT[i]), gm)      # no roll-over
+    assert int(m.latest_time) == int(quads[i, 3])
+    assert torch.equal(sp1, sp2) and torch.equal(op1, op2) and float(l1) == float(l2)
+    # and it is NOT what the reference returns for that call
+    k = int(np.flatnonzero(ctx['ev']['te'] == i)[0])
+    assert abs(float(l1) - float(ctx['ev']['loss'][k])) > 1e-3
