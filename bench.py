@@ -34,6 +34,16 @@ import time
 if os.environ.get('OMP_NUM_THREADS') == '1' and 'LOCAL_RANK' in os.environ:
     os.environ['OMP_NUM_THREADS'] = '8'
 
+# Under a cgroup CPU quota far below the visible core count (16-24 CPUs of 128 on the GPU boxes) an OpenMP pool sized by
+# the core count only burns the quota in spin-waits: size it by the quota.
+if 'OMP_NUM_THREADS' not in os.environ:
+    try:
+        _q, _per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if _q != 'max':
+            os.environ['OMP_NUM_THREADS'] = str(max(1, int(float(_q) / float(_per))))
+    except Exception:
+        pass
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
