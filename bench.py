@@ -442,6 +442,7 @@ def run_ours(args):
         # consumer thread (a plan takes ~0.6 ms of one core, a step needs two: 2 threads keep up with a 1.3 ms step)
         quota = _cpu_quota()
         E2E_DEPTH = 4
+        hoststore.reserve_pinned(4 * (E2E_DEPTH + 3))     # every staging buffer the loader can need, pinned up front
         E2E_WORKERS = 8 if not quota else max(2, min(8, int(quota / max(world, 1)) - 2))
         k_e2e = max(4, args.steps)
         h2d, d2h, msgs, dt = run_e2e(max(3, args.warmup), k_e2e, 0)

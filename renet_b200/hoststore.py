@@ -156,6 +156,13 @@ _staging = {}
 _PINNED_POOL = __import__('collections').deque()
 
 
+def reserve_pinned(n, words=1 << 21):
+    """Make sure the process-wide pool holds at least ``n`` pinned staging buffers.  Pinning is expensive (cudaHostAlloc
+    of 8 MB: 4-10 ms, and it can stall the device), so a loader should never have to do it in the middle of a run."""
+    while len(_PINNED_POOL) < n:
+        _PINNED_POOL.append(torch.empty(words, dtype=torch.int32).pin_memory())
+
+
 def assemble_view_raw(view, out, sort=True):
     """Run the C++ batcher into the int32 numpy buffer ``out`` (host only, no CUDA).  Returns None when
     the buffer is too small (sizes[6] words are needed), else a dict of sizes + small host arrays."""
@@ -464,6 +471,7 @@ def prefetch(view_groups, device, depth=2, workers=4, sort=True, inner_threads=1
     if inner_threads is not None:          # many concurrent batcher calls: fewer threads inside each
         prev_threads = _lib.lib().renet_set_host_threads(int(inner_threads))
     free = _PINNED_POOL          # pinned staging buffers are expensive to create (~4 ms each): pooled per process
+    reserve_pinned(2 * (depth + 3) + 2)      # two views per step in flight for depth steps + uploads not yet retired
     loader = NativeLoader(workers)
     pending = collections.deque()
     it = iter(view_groups)
