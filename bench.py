@@ -425,7 +425,9 @@ def run_ours(args):
                 a, b, ev = api_step(e, hbs, out_ring[i & 1])
                 if i >= n_warm:
                     h2d += a; d2h += b
-                    graphs.extend(hb.graph for hb in hbs)      # edge counts come back asynchronously: summed after the loop
+                    # edge counts come back asynchronously and are summed after the loop; only the tiny handles are kept,
+                    # so every batch's device memory returns to the allocator when its step is done
+                    graphs.extend(hb.graph.edge_count_handle() for hb in hbs)
                 if prev is not None:
                     prev[0].synchronize()
                     checksum += float(prev[1][0, 0])
@@ -435,7 +437,7 @@ def run_ours(args):
                 checksum += float(prev[1][0, 0])
             barrier()
             dt = time.perf_counter() - t0
-            msgs = sum(2 * g.E for g in graphs)
+            msgs = sum(2 * g.value() for g in graphs)
             return h2d, d2h, msgs, dt
 
         # loader threads per rank: 8 when the host has room; under a cgroup CPU quota leave a core per rank for the

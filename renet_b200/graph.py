@@ -111,6 +111,31 @@ def as_history_graph(g):
     return hg
 
 
+class PendingCount:
+    """An integer the GPU produces: (event, pinned int32[1]) of an asynchronous device->host read-back; value() waits
+    for the event once, caches the number and hands the pinned slot back to its pool."""
+
+    def __init__(self, event, pinned, release=None):
+        self._ev, self._pinned, self._release, self._v = event, pinned, release, None
+
+    def value(self):
+        if self._v is None:
+            self._ev.synchronize()
+            self._v = int(self._pinned[0])
+            if self._release is not None:
+                self._release(self._pinned)
+            self._ev = self._pinned = self._release = None
+        return self._v
+
+
+class _KnownCount:
+    def __init__(self, v):
+        self._v = int(v)
+
+    def value(self):
+        return self._v
+
+
 class BatchedHistoryGraph:
     """Disjoint union of induced sub-graphs, device-resident, CSR by destination.
 
@@ -172,20 +197,20 @@ class BatchedHistoryGraph:
     # ---- edge count: known on the host for host-assembled batches; for device-assembled ones (hoststore, device
     # batcher) it is produced on the GPU and read back lazily, so nothing on the forward path waits for it ------------
     _E = None
-    _E_pending = None       # (event, pinned int32[1], release callback) of the asynchronous read-back
+    _E_pending = None       # PendingCount of the asynchronous read-back (device-assembled batches)
     E_cap = None            # capacity of the col_* arrays (>= E); launch argument while E is still in flight
 
     @property
     def E(self):
         if self._E is None:
-            ev, pinned, release = self._E_pending
-            ev.synchronize()
-            self._E = int(pinned[0])
+            self._E = self._E_pending.value()
             self._E_pending = None
-            if release is not None:
-                release(pinned)
             self.col_src, self.col_type_s, self.col_type_o = (x[:self._E] for x in (self.col_src, self.col_type_s, self.col_type_o))
         return self._E
+
+    def edge_count_handle(self):
+        """Something with ``.value()`` that yields E later WITHOUT keeping the graph (and its device memory) alive."""
+        return self._E_pending if self._E is None else _KnownCount(self._E)
 
     @E.setter
     def E(self, v):

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .graph import BatchedHistoryGraph, _Frame, as_history_graph
+from .graph import BatchedHistoryGraph, PendingCount, _Frame, as_history_graph
 from .utils import HistoryBatch
 
 MAX_LEN = 16
@@ -360,7 +360,7 @@ def _upload_plan(view, buf, r, device):
     blob.record_stream(main)
     g = BatchedHistoryGraph.__new__(BatchedHistoryGraph)
     g.device, g.N = torch.device(device), N
-    g._E_pending, g.E_cap = (e_ev, e_host, _E_PINNED.append), E_cand
+    g._E_pending, g.E_cap = PendingCount(e_ev, e_host, _E_PINNED.append), E_cand
     g.node_ent, g.row_ptr = d['node_ent'], parts['row_ptr']
     g.col_src, g.col_type_s, g.col_type_o = parts['col_src'], parts['col_type_s'], parts['col_type_o']
     g.norm = parts['norm'].view(torch.float32)
