@@ -129,7 +129,15 @@ class ClockSampler:
     def stop(self):
         if self.t is not None:
             self._stop.set()
-            self.t.join(timeout=1)
+            self.t.join(timeout=5)
+            if not self.t.is_alive():
+                # leave nothing of NVML behind in this process: the end-to-end loop that follows is bound by CUDA API
+                # calls on the host, and an initialised NVML client shares driver locks with them
+                try:
+                    import pynvml
+                    pynvml.nvmlShutdown()
+                except Exception:
+                    pass
             return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.max_mhz,
                     'samples': len(self.sm), 'reasons': sorted(self.reasons), 'source': 'nvml, polled every 2 ms'}
         try:
