@@ -228,3 +228,86 @@ def test_native_loader_jobs_equal_synchronous_calls():
     small = ld.finish(ld.submit(hs.select(sels[0]), np.zeros(8, np.int32), True, True))
     assert small == {'need_words': sync and hoststore.plan_view_raw(hs.select(sels[0]), np.zeros(8, np.int32))['need_words']}
     ld.close()
+
+
+def test_lazy_edge_count_resolves_once_and_trims_columns():
+    """BatchedHistoryGraph.E of a device-assembled batch: produced on the GPU, read back asynchronously (PendingCount);
+    E_launch never waits, E / edge_count_handle() wait once, trim the capacity-sized columns and release the slot once."""
+    import torch
+    from renet_b200.graph import BatchedHistoryGraph, PendingCount
+
+    class FakeEvent:
+        def __init__(self):
+            self.syncs = 0
+
+        def synchronize(self):
+            self.syncs += 1
+
+    released = []
+    ev, pinned = FakeEvent(), torch.tensor([5], dtype=torch.int32)
+    g = BatchedHistoryGraph.__new__(BatchedHistoryGraph)
+    g.N, g.E_cap = 3, 9
+    g._E_pending = PendingCount(ev, pinned, released.append)
+    g.col_src, g.col_type_s, g.col_type_o = (torch.arange(9, dtype=torch.int32) for _ in range(3))
+    assert g.E_launch == 9 and ev.syncs == 0                 # launch argument: the capacity bound, no wait
+    h = g.edge_count_handle()
+    assert g.E == 5 and ev.syncs == 1 and len(released) == 1
+    assert g.E_launch == 5 and g.number_of_edges() == 5
+    assert [len(x) for x in (g.col_src, g.col_type_s, g.col_type_o)] == [5, 5, 5]
+    assert h.value() == 5 and ev.syncs == 1 and len(released) == 1      # the handle shares the resolved count
+    assert g.edge_count_handle().value() == 5
+    # handle first, graph later (bench.py keeps only handles and lets the batch go)
+    ev2 = FakeEvent()
+    g2 = BatchedHistoryGraph.__new__(BatchedHistoryGraph)
+    g2.N, g2.E_cap = 3, 4
+    g2._E_pending = PendingCount(ev2, torch.tensor([2], dtype=torch.int32), released.append)
+    g2.col_src, g2.col_type_s, g2.col_type_o = (torch.arange(4, dtype=torch.int32) for _ in range(3))
+    h2 = g2.edge_count_handle()
+    assert h2.value() == 2 and g2.E == 2 and ev2.syncs == 1 and len(released) == 2
+    # host-assembled batch: the count is known from the start
+    g3 = BatchedHistoryGraph.__new__(BatchedHistoryGraph)
+    g3.E = 7
+    assert g3.E == 7 and g3.E_launch == 7 and g3.edge_count_handle().value() == 7
+
+
+def test_batchers_agree_on_random_batches_sorted_and_unsorted():
+    """Randomised cross-check of the three host paths (numpy, C++ all-host, C++ plan + induced-edge filter) on batches
+    with duplicate samples, mixed empty histories, tiny and large sizes, in both sample orders (utils.py:209-244 sorts by
+    history length, :246-283 keeps the given order and needs the non-empty histories first)."""
+    from renet_b200 import hoststore
+    quads, num_e, num_r = synthetic.make_quads('icews18', seed=23, num_timestamps=12)
+    S, ST, O, OT = synthetic.build_history(quads)
+    gd = synthetic.build_graph_dict(quads, num_r)
+    gs = hoststore.GraphStore(gd)
+    hs = hoststore.HistoryStore(S, ST, quads[:, 0], gs)
+    lens = np.asarray([len(x) for x in S])
+    rng = np.random.RandomState(77)
+    for trial in range(12):
+        B = int(rng.choice([1, 2, 7, 64, 400]))
+        sel = rng.randint(0, len(quads), B)                     # duplicates allowed
+        for sort in (True, False):
+            if not sort:                                        # unsorted twin: non-empty histories first
+                sel = np.concatenate((sel[lens[sel] > 0], sel[lens[sel] == 0]))
+            view = hs.select(sel)
+            ref = utils.assemble_history_batch_host([S[i] for i in sel], [ST[i] for i in sel], quads[sel][:, 0], gd, sort)
+            buf = np.zeros(1 << 20, np.int32)
+            r = hoststore.assemble_view_raw(view, buf, sort)
+            pbuf = np.zeros(1 << 20, np.int32)
+            pr = hoststore.plan_view_raw(view, pbuf, sort)
+            assert r['S'] == pr['S'] == ref.S
+            if ref.S == 0:
+                continue
+            a, p = hoststore.split_raw(buf, r), hoststore.split_plan(pbuf, pr)
+            ind = _induce_numpy(gs, p)
+            g = ref.graph
+            np.testing.assert_array_equal(r['s_idx'], ref.s_idx)
+            np.testing.assert_array_equal(pr['s_idx'], ref.s_idx)
+            for k in ('node_ent', 'row_ptr', 'col_src', 'col_type_s', 'col_type_o'):
+                np.testing.assert_array_equal(a[k], g[k].astype(np.int32), err_msg=k)
+            for k in ('row_ptr', 'col_src', 'col_type_s', 'col_type_o'):
+                np.testing.assert_array_equal(ind[k], a[k], err_msg=k)
+            np.testing.assert_array_equal(p['node_ent'], a['node_ent'])
+            np.testing.assert_array_equal(ind['norm'], g['norm'])
+            for k in ('readout', 'row_comp', 'row_seq', 'seq_start', 'seq_len', 'packed_row'):
+                np.testing.assert_array_equal(p[k], a[k], err_msg=k)
+            np.testing.assert_array_equal(pr['batch_sizes'], ref.batch_sizes)
