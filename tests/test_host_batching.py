@@ -311,3 +311,31 @@ def test_batchers_agree_on_random_batches_sorted_and_unsorted():
             for k in ('readout', 'row_comp', 'row_seq', 'seq_start', 'seq_len', 'packed_row'):
                 np.testing.assert_array_equal(p[k], a[k], err_msg=k)
             np.testing.assert_array_equal(pr['batch_sizes'], ref.batch_sizes)
+
+
+def test_view_from_lists_equals_numpy_path_and_store_path():
+    """hoststore.view_from_lists: a batch given as the reference's Python lists, flattened on the fly (no de-duplication),
+    produces the numpy path's batch through the C++ batcher; unknown timestamps / entities raise KeyError."""
+    import pytest
+    from renet_b200 import hoststore
+    quads, num_e, num_r = synthetic.make_quads('icews18', seed=5, num_timestamps=14)
+    S, ST, O, OT = synthetic.build_history(quads)
+    gd = synthetic.build_graph_dict(quads, num_r)
+    gs = hoststore.GraphStore(gd)
+    sel = np.random.RandomState(2).permutation(len(quads))[:256]
+    for hist, hist_t, col in ((S, ST, 0), (O, OT, 2)):
+        h, ht, subj = [hist[i] for i in sel], [hist_t[i] for i in sel], quads[sel][:, col]
+        view = hoststore.view_from_lists(h, ht, subj, gs)
+        buf = np.zeros(1 << 20, np.int32)
+        r = hoststore.assemble_view_raw(view, buf)
+        got = hoststore.split_raw(buf, r)
+        ref = utils.assemble_history_batch_host(h, ht, subj, gd)
+        np.testing.assert_array_equal(r['s_idx'], ref.s_idx)
+        for k in ('node_ent', 'row_ptr', 'col_src', 'col_type_s', 'col_type_o'):
+            np.testing.assert_array_equal(got[k], ref.graph[k].astype(np.int32), err_msg=k)
+        np.testing.assert_array_equal(got['readout'], np.asarray(ref.readout[0]).astype(np.int32))
+    with pytest.raises(KeyError):
+        hoststore.view_from_lists([[np.asarray([[0, 1]])]], [[10 ** 9]], [1], gs)          # unknown timestamp
+    t0 = int(gs.times[0])
+    with pytest.raises(KeyError):
+        hoststore.view_from_lists([[np.asarray([[0, num_e + 5]])]], [[t0]], [int(gs.node_ent[0])], gs)   # unknown entity
