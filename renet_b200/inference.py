@@ -240,3 +240,37 @@ class RENetInference:
             pred[label] = ground
             ranks.append(rank_with_ties(pred, label))
         return np.array(ranks), loss
+
+    def evaluate_stream(self, test_data, s_history, o_history, global_model, total_data=None, raw=False):
+        """The reference's test loop (test.py:98-150) as a method: trims the per-entity histories to ``seq_len``
+        (test.py:100-106), ranks every test triple in stream order (``evaluate`` when ``raw`` else ``evaluate_filter``
+        against ``total_data``), and returns MRR / MR / Hits@{1,3,10} over subject and object ranks together, the summed
+        loss and the ranks.  ``s_history`` / ``o_history`` = (lists, timestamp lists) of the test split."""
+        for hist, hist_t in ((self.s_hist_test, self.s_hist_test_t), (self.o_hist_test, self.o_hist_test_t)):
+            for ee in range(self.in_dim):
+                while len(hist[ee]) > self.seq_len:
+                    hist[ee].pop(0)
+                    hist_t[ee].pop(0)
+        test_data = torch.as_tensor(test_data)
+        if not raw:
+            if total_data is None:
+                raise ValueError('filtered evaluation needs total_data (all known triples)')
+            total_data = torch.as_tensor(total_data).to(self.ent_embeds.device)
+        ranks, total_loss = [], 0.0
+        with torch.no_grad():
+            for i in range(len(test_data)):
+                trip = test_data[i].to(self.ent_embeds.device)
+                sh, oh = (s_history[0][i], s_history[1][i]), (o_history[0][i], o_history[1][i])
+                if raw:
+                    r, loss = self.evaluate(trip, sh, oh, global_model)
+                else:
+                    r, loss = self.evaluate_filter(trip, sh, oh, global_model, total_data)
+                ranks.append(r)
+                total_loss += float(loss)
+        ranks = np.concatenate(ranks) if ranks else np.zeros(0)
+        out = {'mrr': float(np.mean(1.0 / ranks)) if len(ranks) else float('nan'),
+               'mr': float(np.mean(ranks)) if len(ranks) else float('nan'), 'loss': total_loss, 'ranks': ranks}
+        for k in (1, 3, 10):
+            out['hits@%d' % k] = float(np.mean(ranks <= k)) if len(ranks) else float('nan')
+        return out
+

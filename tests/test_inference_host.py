@@ -76,3 +76,23 @@ def test_rebinding_switch_scores_the_triple_itself():
     # and it is NOT what the reference returns for that call
     k = int(np.flatnonzero(ctx['ev']['te'] == i)[0])
     assert abs(float(l1) - float(ctx['ev']['loss'][k])) > 1e-3
+
+
+def test_evaluate_stream_metrics_match_reference_ranks():
+    """RENet.evaluate_stream (the reference's test.py loop) reproduces MRR / MR / Hits from the reference's own filtered
+    ranks of the golden run (test.py:140-150 formulas)."""
+    ctx = eval_setup('cpu')
+    m, ev, quads, gm = ctx['model'], ctx['ev'], ctx['quads'], ctx['gm']
+    m.aggregator.encode = _oracle_encode(ctx)
+    S, ST, O, OT = ctx['hist']
+    te = ev['te']
+    m.latest_time = torch.tensor(ctx['t_test'])
+    torch.manual_seed(1234)
+    out = m.evaluate_stream(quads[te], ([S[i] for i in te], [ST[i] for i in te]), ([O[i] for i in te], [OT[i] for i in te]),
+                            gm, total_data=quads)
+    ref = ev['filt'].reshape(-1)
+    np.testing.assert_array_equal(out['ranks'], ref)
+    assert abs(out['mrr'] - np.mean(1.0 / ref)) < 1e-12 and abs(out['mr'] - np.mean(ref)) < 1e-12
+    for k in (1, 3, 10):
+        assert out['hits@%d' % k] == float(np.mean(ref <= k))
+    assert abs(out['loss'] - float(ev['loss'].sum())) < 1e-3 * float(ev['loss'].sum())
