@@ -455,7 +455,9 @@ def run_ours(args):
         hoststore.reserve_pinned(4 * (E2E_DEPTH + 3))     # every staging buffer the loader can need, pinned up front
         E2E_WORKERS = 8 if not quota else max(2, min(8, int(quota / max(world, 1)) - 2))
         k_e2e = max(4, args.steps)
-        w_e2e = max(6, args.warmup)       # the loader, the pinned pool and the allocator cache reach steady state
+        # one full rotation over the pool of batches: the loader, the pinned pool and the caching allocator (whose block
+        # sizes depend on the batch) have reached steady state before the clock starts
+        w_e2e = max(len(pool) + 1, args.warmup)
         h2d, d2h, msgs, dt = run_e2e(w_e2e, k_e2e, 0)
         tt = torch.tensor([dt, float(msgs)], device=dev, dtype=torch.float64)
         if world > 1:
