@@ -66,6 +66,11 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--host-batcher', action='store_true', help='e2e with the all-host C++ batcher instead of the device batcher')
+    ap.add_argument('--mode', default='aggregate', choices=['aggregate', 'train'],
+                    help="aggregate: the BASELINE metric line (it also carries a 'train' object); train: only the training-step region, "
+                         "as the line's value")
+    ap.add_argument('--no-train', action='store_true', help='skip the training-step region of the default line')
+    ap.add_argument('--dropout', type=float, default=0.0, help='dropout of the training-step region (reference default 0.5)')
     return ap.parse_args()
 
 
@@ -234,6 +239,77 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+
+# ------------------------------------------------------------------------------------------------------
+def train_region(args, tkg, pool, global_emb, dev, world, torch, dist):
+    """One reference training step per iteration (train.py:136-143) on this rank's shard of the global batch
+    (1024 samples per rank, global batch 1024 x world): RENet.forward x2 directions -> backward through the CUDA
+    backward kernels -> gradient all-reduce (NCCL, bucketed, launched from autograd hooks while backward still runs)
+    -> clip_grad_norm_ -> Adam (csrc/optim.cu).  Device-timed over pre-built batches resident in HBM, rotating over the
+    pool; the backward graph structures (CSR by source, relation-grouped edges) are rebuilt every step, as for a fresh
+    batch.  Phase times come from CUDA events on the compute stream: `allreduce_exposed_ms` is the time that stream
+    spends waiting for NCCL after the last backward kernel."""
+    from renet_b200 import _lib
+    from renet_b200.model import RENet
+    from renet_b200.parallel import DataParallelTrainer
+    torch.manual_seed(999)
+    model = RENet(tkg.num_e, H_DIM, tkg.num_r, dropout=args.dropout).to(dev).train()
+    model.global_emb = global_emb
+    tr = DataParallelTrainer(model, lr=1e-3, weight_decay=1e-5, grad_norm=1.0, record_events=True)
+    for e in pool:
+        if 'q_dev' not in e:
+            e['q_dev'] = torch.from_numpy(e['q']).to(dev)
+
+    def one(e):
+        for d in e['dirs']:
+            d['hb'].graph._bwd = {}
+        return tr.train_step(e['q_dev'], e['dirs'][0]['hb'], e['dirs'][1]['hb'], tkg.graph_dict)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warm = max(3, args.warmup)
+    for i in range(warm):
+        one(pool[i % len(pool)])
+    barrier()
+    n0 = _lib.launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    evs, msgs, losses = [], 0, []
+    for i in range(args.steps):
+        e = pool[(warm + i) % len(pool)]
+        losses.append(one(e))
+        evs.append(tr.last_events)
+        msgs += sum(2 * d['g'].E for d in e['dirs'])
+    end.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms = start.elapsed_time(end)
+    phases = np.zeros(4)
+    for ev in evs:
+        phases += [ev[k].elapsed_time(ev[k + 1]) for k in range(4)]
+    phases /= len(evs)
+    t = torch.tensor([ms, float(msgs)] + list(phases), device=dev, dtype=torch.float64)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, msgs = tmax[0].item(), tsum[1].item()
+        phases = tmax[2:].cpu().numpy()
+    loss = float(torch.stack(losses).mean())
+    tr.close()
+    return {'value': msgs / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / args.steps, 'steps': args.steps, 'warmup': warm,
+            'forward_ms': float(phases[0]), 'backward_ms': float(phases[1]), 'allreduce_exposed_ms': float(phases[2]),
+            'optimizer_ms': float(phases[3]), 'global_batch': BATCH * world, 'dropout': args.dropout,
+            'grad_bytes_allreduced_per_step': int(tr.total * 4) if world > 1 else 0, 'buckets': len(tr.buckets),
+            'collective': ('nccl all_reduce(sum) of the flat fp32 gradient in %d buckets, launched from autograd hooks during '
+                           'backward' % len(tr.buckets)) if world > 1 else 'none (1 GPU)',
+            'gpu_launches': int(launches), 'mean_loss': loss,
+            'what': 'train.py:136-143 per rank: RENet.forward x2 directions (RGCN x2 + fused read-out/GRU + decoder/CE) -> backward '
+                    '-> gradient all-reduce -> clip_grad_norm_(1.0) -> Adam(lr 1e-3, wd 1e-5); phase times are max over ranks'}
+
+
 # ------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -281,6 +357,21 @@ def run_ours(args):
         pool.append(entry)
     msgs_per_step = [sum(2 * d['g'].E for d in e['dirs']) for e in pool]
     pool_bytes = sum(sum(d['g'].E * 12 + d['g'].N * (8 + 1600) for d in e['dirs']) for e in pool)
+    if args.mode == 'train':
+        clocks = ClockSampler(local)
+        clocks.start()
+        train = train_region(args, tkg, pool, model.global_emb, dev, world, torch, dist)
+        clk = clocks.stop()
+        if rank == 0:
+            print(json.dumps({'metric': 'training_step_edge_messages_per_sec', 'value': train['value'], 'unit': UNIT, 'n_gpus': world,
+                              'steps': args.steps, 'warmup': train['warmup'], 'ms_per_step': train['ms_per_step'],
+                              'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                              'config': {'workload': WORKLOAD, 'global_batch': BATCH * world, 'l2': 'rotating-pool',
+                                         'pool_batches': len(pool), 'parallelism': 'dp%d (replicated parameters, NCCL gradient all-reduce)' % world},
+                              'clocks': clk, 'gpu_launches': train['gpu_launches'], 'train': train}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     W1, L1, W2, L2 = (agg.rgcn1.weight.detach(), agg.rgcn1.loop_weight.detach(), agg.rgcn2.weight.detach(),
                       agg.rgcn2.loop_weight.detach())
     P = _lib.ptr
@@ -474,6 +565,14 @@ def run_ours(args):
                        'direction + induced-edge CSR build on the GPU + RGCN x2 + fused read-out/GRU + pinned D2H of the '
                        '[B,2h] outputs every step (read one step behind the enqueue front)'}
 
+    train = None
+    if not args.no_train:
+        try:
+            train = train_region(args, tkg, pool, model.global_emb, dev, world, torch, dist)
+        except Exception as ex:          # the aggregate metric does not depend on it; a failure is reported, not hidden
+            import traceback
+            train = {'failed': '%s: %s' % (type(ex).__name__, ex), 'trace': traceback.format_exc()[-1500:]}
+
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_sample(tkg, torch, 3, 1)
@@ -489,7 +588,7 @@ def run_ours(args):
                            'edge_msgs_per_step': msgs_per_step[0], 'l2': 'rotating-pool', 'pool_batches': len(pool),
                            'pool_bytes': int(pool_bytes), 'parallelism': 'dp%d (independent shards, no data-path collective)' % world},
                 'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
-                'gru_ms_one_direction': gru_ms}
+                'gru_ms_one_direction': gru_ms, 'train': train}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -350,6 +350,24 @@ int renet_pack_inputs(const float* H2, const int32_t* readout, const int32_t* ro
                       const int32_t* packed_row, float* X4, float* X3,
                       int64_t S, int32_t h, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser step of the reference training loop on FLAT fp32 buffers (reference train.py:140-142:
+ * torch.nn.utils.clip_grad_norm_(model.parameters(), grad_norm); Adam(lr, weight_decay).step()).  The data-parallel
+ * engine keeps all parameters / gradients as views into one flat buffer each (the gradient buffer is what NCCL
+ * all-reduces), so the step is two HBM-bound launches.
+ *   renet_grad_sumsq : out[0] (=|+=) sum(grad[i]^2), fixed-order reduction (reproducible, no float atomics);
+ *                      workspace: renet_grad_sumsq_workspace_bytes() bytes.
+ *   renet_adam_step  : g = grad*grad_scale*clip (+ weight_decay*param);  clip = min(1, max_norm/(sqrt(sumsq[0])*grad_scale
+ *                      + 1e-6)) when sumsq != NULL and max_norm > 0, else 1;  m,v moments; bias correction with `step`
+ *                      (counts from 1); param updated in place.  Matches torch.optim.Adam (amsgrad=False).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t renet_grad_sumsq_workspace_bytes(void);
+int renet_grad_sumsq(const float* grad, int64_t n, float* out, int32_t accumulate, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+int renet_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int64_t step, const float* sumsq,
+                    float max_norm, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

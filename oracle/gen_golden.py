@@ -347,6 +347,78 @@ def gen_graph_kats(ns):
     print('graph_kats.npz')
 
 
+def _ref_model(ns, quads, num_e, R, h, nb, seed):
+    gd = {}
+    for t in np.unique(quads[:, 3]):
+        gd[int(t)] = ns.utils.get_big_graph(quads[quads[:, 3] == t][:, :3], R)
+    m = ns.model.RENet(num_e, h, R, dropout=0, model=0, seq_len=10, num_k=10)
+    if nb != 100:
+        m.aggregator = ns.Aggregator.RGCNAggregator(h, 0, num_e, R, nb, 0, 10)
+    m.load_state_dict(det_params(RENET_SHAPES(num_e, h, R, nb), seed), strict=True)
+    m.global_emb = det_global_emb(np.unique(quads[:, 3]), h, seed + 1)
+    return m, gd
+
+
+def gen_aggregator_predict(ns):
+    """RGCNAggregator.forward (ELEMENT-wise packed inputs), .predict_batch and .predict (Aggregator.py:124-237) run by
+    the unmodified reference: on the tiny stream (h=8, every element stored) and on the real ICEWS18 slice (h=200:
+    predict fully; predict_batch called the way model.py:172-191 calls it -- num_rels copies of one history -- of which
+    the rows of copies 0, 1 and R-1 and the column sums of all rows are stored)."""
+    from oracle import restate
+    tiny = np.load(os.path.join(OUT, 'renet_tiny.npz'))
+    slc = np.load(os.path.join(OUT, 'renet_icews18_slice.npz'))
+    blob = {}
+    for tag, b in (('tiny', tiny), ('slice', slc)):
+        quads = b['quads'].astype(np.int64)
+        num_e, R, h, nb, seed = int(b['num_e']), int(b['R']), int(b['h']), int(b['nb']), int(b['seed'])
+        sel = b['sel']
+        with ref_loader.cpu_patches():
+            m, gd = _ref_model(ns, quads, num_e, R, h, nb, seed)
+            S, ST, O, OT = restate.build_history(quads, num_e)
+            batch = torch.from_numpy(quads[sel]).long()
+            for d, subj in (('subj', True), ('obj', False)):
+                hist = ([S[i] for i in sel], [ST[i] for i in sel]) if subj else ([O[i] for i in sel], [OT[i] for i in sel])
+                rel = m.rel_embeds[:R] if subj else m.rel_embeds[R:]
+                s = batch[:, 0] if subj else batch[:, 2]
+                r = batch[:, 1]
+                with torch.no_grad():
+                    if tag == 'tiny':
+                        p4, p3 = m.aggregator(hist, s, r, m.ent_embeds, rel, gd, m.global_emb, not subj)
+                        blob['%s/%s/fwd_x4' % (tag, d)] = p4.data.numpy().copy()
+                        blob['%s/%s/fwd_x3' % (tag, d)] = p3.data.numpy().copy()
+                        blob['%s/%s/fwd_bs' % (tag, d)] = p4.batch_sizes.numpy().copy()
+                        # predict_batch on different histories whose lengths already descend (it never sorts, utils.py:251)
+                        lens = np.asarray([len(x) for x in hist[0]])
+                        order = [int(i) for i in np.argsort(-lens, kind='stable') if lens[i] > 0][:12]
+                        hb = ([hist[0][i] for i in order], [hist[1][i] for i in order])
+                        q4, q3 = m.aggregator.predict_batch(hb, s[order], r[order], m.ent_embeds, rel, gd, m.global_emb, not subj)
+                        blob['%s/%s/pb_order' % (tag, d)] = np.asarray(order)
+                        blob['%s/%s/pb_x4' % (tag, d)] = q4.data.numpy().copy()
+                        blob['%s/%s/pb_x3' % (tag, d)] = q3.data.numpy().copy()
+                        blob['%s/%s/pb_bs' % (tag, d)] = q4.batch_sizes.numpy().copy()
+                    # the sample with the longest history: predict, and predict_batch as pred_r_rank2 calls it
+                    lens = np.asarray([len(x) for x in hist[0]])
+                    k = int(np.argmax(lens))
+                    blob['%s/%s/k' % (tag, d)] = np.int64(k)
+                    inp, inp_r = m.aggregator.predict((hist[0][k], hist[1][k]), s[k], r[k], m.ent_embeds, rel, gd,
+                                                      m.global_emb, not subj)
+                    blob['%s/%s/pred_x4' % (tag, d)] = inp.numpy().copy()
+                    blob['%s/%s/pred_x3' % (tag, d)] = inp_r.numpy().copy()
+                    ss = s[k].repeat(R)
+                    rr = torch.arange(R)
+                    q4, q3 = m.aggregator.predict_batch(([hist[0][k]] * R, [hist[1][k]] * R), ss, rr, m.ent_embeds, rel, gd,
+                                                        m.global_emb, not subj)
+                    L = int(lens[k])
+                    rows = np.asarray([t * R + q for t in range(L) for q in (0, 1, R - 1)])
+                    blob['%s/%s/rank_rows' % (tag, d)] = rows
+                    blob['%s/%s/rank_x4' % (tag, d)] = q4.data[rows].numpy().copy()
+                    blob['%s/%s/rank_x3' % (tag, d)] = q3.data[rows].numpy().copy()
+                    blob['%s/%s/rank_x4_sum' % (tag, d)] = q4.data.double().sum(0).numpy()
+                    blob['%s/%s/rank_bs' % (tag, d)] = q4.batch_sizes.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, 'aggregator_predict.npz'), **blob)
+    print('aggregator_predict.npz:', len(blob), 'arrays')
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
@@ -356,3 +428,4 @@ if __name__ == '__main__':
     gen_renet_tiny(ns)
     gen_renet_icews18_slice(ns)
     gen_renet_eval_tiny(ns)
+    gen_aggregator_predict(ns)

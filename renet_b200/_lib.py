@@ -51,6 +51,9 @@ SIGNATURES = {
     'renet_loader_wait': (ctypes.c_int, [_vp, _i64]),
     'renet_prepare_sequences': (ctypes.c_int, [_vp, _i32, _i32, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'renet_pack_inputs': (ctypes.c_int, [_vp] * 12 + [_i64, _i32, _vp]),
+    'renet_grad_sumsq_workspace_bytes': (_i64, []),
+    'renet_grad_sumsq': (ctypes.c_int, [_vp, _i64, _vp, _i32, _vp, _i64, _vp]),
+    'renet_adam_step': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64] + [ctypes.c_float] * 5 + [_i64, _vp, ctypes.c_float, ctypes.c_float, _vp]),
 }
 
 _lib = None
@@ -125,13 +128,24 @@ def new_pack_token():
     return next(_pack_tokens)
 
 
+_weight_epoch = [0]
+
+
+def invalidate_packed_weights():
+    """Declare that weights may have changed in a way the in-place version counters do not see (updates through
+    ``p.data``, raw-pointer optimiser kernels, load_state_dict into re-pointed storage ...): every packed image made so
+    far becomes stale.  Pure host bookkeeping -- the epoch is part of every weight generation."""
+    _weight_epoch[0] += 1
+
+
 class weight_generation:
     """Context manager: while active, the tcgen05 GEMM engine may reuse packed weight images made under the same
-    generation = hash(module token, (address, in-place version) of every weight).  Outside of it the cache is off, so
-    direct C-ABI callers are never served a stale image."""
+    generation = hash(module token, invalidation epoch, (address, in-place version) of every weight).  Outside of it the
+    cache is off, so direct C-ABI callers are never served a stale image.  Only version-bumping in-place updates are
+    tracked automatically; anything else must call ``invalidate_packed_weights()`` (the trainer in parallel.py does)."""
 
     def __init__(self, token, params):
-        self.gen = hash((token,) + tuple((p.data_ptr(), p._version) for p in params)) & ((1 << 62) - 1)
+        self.gen = hash((token, _weight_epoch[0]) + tuple((p.data_ptr(), p._version) for p in params)) & ((1 << 62) - 1)
 
     def __enter__(self):
         lib().renet_set_weight_generation(self.gen)

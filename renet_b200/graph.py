@@ -233,6 +233,7 @@ class BatchedHistoryGraph:
 
     def coo_dst(self):
         if 'dst' not in self._bwd:
+            self.E          # device-assembled batch: resolve the asynchronous edge count first (trims col_* to E entries)
             counts = (self.row_ptr[1:] - self.row_ptr[:-1]).long()
             self._bwd['dst'] = torch.repeat_interleave(
                 torch.arange(self.N, device=self.device, dtype=torch.int32), counts)
@@ -242,6 +243,9 @@ class BatchedHistoryGraph:
         """(t_row_ptr, t_col_dst, t_col_type, rel_ptr, rel_src, rel_dst) for the backward kernels."""
         key = ('bwd', bool(reverse), int(num_types))
         if key not in self._bwd:
+            # the device batcher returns E asynchronously and leaves col_* at capacity E_cand with an uninitialised tail:
+            # reading self.E waits for the count and trims the columns, so build_csr never sees the tail
+            assert self.E == int(self.col_src.numel())
             dst = self.coo_dst()
             et = self.col_type(reverse)
             t_row_ptr, t_col_dst, t_col_type, _ = build_csr(self.col_src, dst, et, self.N)

@@ -214,7 +214,11 @@ def global_rows(global_emb, times, h, device):
     read-out row with a .cpu() each (utils.py:224-225); here the dict is turned into a dense device table
     once (cached per dict object) and a batch is one index_select."""
     table, keys = _global_table(global_emb, h, device)
-    idx = np.searchsorted(keys, np.asarray(times, dtype=np.int64))
+    times = np.asarray(times, dtype=np.int64)
+    idx = np.searchsorted(keys, times)
+    bad = (idx >= len(keys)) | (keys[np.minimum(idx, len(keys) - 1)] != times)
+    if np.any(bad):           # the reference indexes the dict and raises KeyError (utils.py:225)
+        raise KeyError(int(times[np.flatnonzero(bad)[0]]))
     return table[torch.from_numpy(idx).to(device)]
 
 

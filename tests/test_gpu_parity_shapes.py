@@ -1,0 +1,178 @@
+"""-m gpu: parity holes named by the round-1 review --
+ * oracle comparison AT THE BENCHMARKED SHAPE (ICEWS18-shaped, 240 timestamps, batch 1024: N ~ 34 k, E ~ 199 k), both
+   directions, forward and backward, and through all batchers (numpy lists, C++ host, device);
+ * GDELT-shaped (thousands of small components) and ICEWS14-shaped batches, forward + backward;
+ * RGCNAggregator.forward ELEMENT-wise, .predict_batch and .predict against goldens written by the unmodified reference
+   (oracle/gen_golden.py:gen_aggregator_predict, reference Aggregator.py:124-237).
+Tolerance 1e-4 relative (max-abs-diff / max-abs-ref), the north-star bar."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_npz, rel_err, t
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DEV = 'cuda:0'
+
+
+def _oracle_two_layers(g, ent, W1, L1, W2, L2, et):
+    dst = np.repeat(np.arange(len(g['node_ent'])), np.diff(g['row_ptr']))
+    args = (t(g['col_src'].astype(np.int64)), t(dst), t(et.astype(np.int64)), t(g['norm']))
+    H0 = ent[t(g['node_ent'].astype(np.int64))]
+    o1 = restate.rgcn_block_layer(H0, W1, L1, *args, True, 100)
+    return o1, restate.rgcn_block_layer(o1, W2, L2, *args, False, 100)
+
+
+def _weights(num_e, R2, seed=0):
+    torch.manual_seed(seed)
+    return (torch.randn(num_e, 200) * 0.1, torch.randn(R2, 400) * 0.1, torch.randn(200, 200) * 0.07,
+            torch.randn(R2, 400) * 0.1, torch.randn(200, 200) * 0.07)
+
+
+@pytest.fixture(scope='module')
+def bench_tkg():
+    from renet_b200 import synthetic
+    return synthetic.SyntheticTKG('icews18', seed=999, num_timestamps=240)
+
+
+def test_bench_shape_both_directions_vs_oracle_all_batchers(bench_tkg):
+    """The exact batch bench.py times (pool entry 0), both directions, 2 layers, against oracle.restate -- through
+    the numpy list path, the C++ host batcher and the device batcher (which must also agree bit for bit)."""
+    import gpu_helpers as G
+    from renet_b200 import hoststore, utils
+    tkg = bench_tkg
+    q, sh, oh = tkg.batch(0, 1024, tail_only=False)
+    sel = tkg.batch_indices(0, 1024, tail_only=False)
+    gs = hoststore.GraphStore(tkg.graph_dict)
+    ent, W1, L1, W2, L2 = _weights(tkg.num_e, 2 * tkg.num_r)
+    dW = [x.to(DEV) for x in (ent, W1, L1, W2, L2)]
+    for hist, hist_all, col, reverse in ((sh, (tkg.s_hist, tkg.s_hist_t), 0, False), (oh, (tkg.o_hist, tkg.o_hist_t), 2, True)):
+        hb_host = utils.assemble_history_batch_host(hist[0], hist[1], q[:, col], tkg.graph_dict)
+        g = hb_host.graph
+        N, E = len(g['node_ent']), len(g['col_src'])
+        assert N > 25000 and E > 150000, (N, E)                       # this IS the bench shape
+        et = g['col_type_o'] if reverse else g['col_type_s']
+        o1, o2 = _oracle_two_layers(g, ent, W1, L1, W2, L2, et)
+        hs = hoststore.HistoryStore(hist_all[0], hist_all[1], tkg.quads[:, col], gs)
+        outs = {}
+        for tag in ('numpy', 'host', 'device'):
+            if tag == 'numpy':
+                hb = utils.assemble_history_batch(hist[0], hist[1], q[:, col], tkg.graph_dict, torch.device(DEV))
+            else:
+                hb = hoststore.assemble_view(hs.select(sel), torch.device(DEV), device_edges=(tag == 'device'))
+            gg = hb.graph
+            assert gg.N == N and gg.E == E, tag
+            h1 = G.layer_fwd(dW[0], gg.node_ent, dW[1], dW[2], gg.row_ptr, gg.col_src, gg.col_type(reverse), gg.norm, N, E,
+                             200, 200, 100, True)
+            h2 = G.layer_fwd(h1, None, dW[3], dW[4], gg.row_ptr, gg.col_src, gg.col_type(reverse), gg.norm, N, E, 200, 200,
+                             100, False)
+            assert rel_err(h1.cpu().numpy(), o1.numpy()) < TOL, (tag, reverse)
+            assert rel_err(h2.cpu().numpy(), o2.numpy()) < TOL, (tag, reverse)
+            outs[tag] = h2
+            np.testing.assert_array_equal(hb.readout.cpu().numpy(), hb_host.readout_host)
+        assert torch.equal(outs['numpy'], outs['host']) and torch.equal(outs['host'], outs['device'])
+
+
+@pytest.mark.parametrize('preset,T,min_G', [('gdelt', 2138, 1800), ('icews14', 181, 150)])
+def test_other_dataset_shapes_fwd_bwd_vs_oracle(preset, T, min_G):
+    """GDELT-shaped (config 3: thousands of small components) and ICEWS14-shaped (config 1) batches of 1024: both RGCN
+    layers forward, and backward (dEnt, dW1, dL1, dW2, dL2) through the CUDA kernels vs torch autograd on the oracle."""
+    import torch.nn.functional as F
+    from renet_b200 import synthetic, utils
+    from renet_b200.rgcn import RGCNBlockLayer
+    tkg = synthetic.SyntheticTKG(preset, seed=999, num_timestamps=T)
+    q, sh, oh = tkg.batch(0, 1024, tail_only=False)
+    hb_host = utils.assemble_history_batch_host(oh[0], oh[1], q[:, 2], tkg.graph_dict)
+    g = hb_host.graph
+    assert len(g['comp_sizes']) >= min_G, len(g['comp_sizes'])
+    R2 = 2 * tkg.num_r
+    ent, W1, L1, W2, L2 = _weights(tkg.num_e, R2, seed=1)
+    P = [p.clone().requires_grad_(True) for p in (ent, W1, L1, W2, L2)]
+    o1, o2 = _oracle_two_layers(g, P[0], P[1], P[2], P[3], P[4], g['col_type_o'])
+    torch.manual_seed(2)
+    Gout = torch.randn(o2.shape)
+    (o2 * Gout).sum().backward()
+    import copy
+    hb = utils.upload_history_batch(copy.copy(hb_host), torch.device(DEV))
+    l1 = RGCNBlockLayer(200, 200, R2, 100, activation=F.relu, self_loop=True).to(DEV)
+    l2 = RGCNBlockLayer(200, 200, R2, 100, activation=None, self_loop=True).to(DEV)
+    with torch.no_grad():
+        l1.weight.copy_(W1); l1.loop_weight.copy_(L1); l2.weight.copy_(W2); l2.loop_weight.copy_(L2)
+    ent_d = ent.to(DEV).requires_grad_(True)
+    h1 = l1.apply_layer(hb.graph, ent_d, hb.graph.node_ent, True)
+    h2 = l2.apply_layer(hb.graph, h1, None, True)
+    assert rel_err(h1.detach().cpu().numpy(), o1.detach().numpy()) < TOL
+    assert rel_err(h2.detach().cpu().numpy(), o2.detach().numpy()) < TOL
+    (h2 * Gout.to(DEV)).sum().backward()
+    got = [ent_d.grad, l1.weight.grad, l1.loop_weight.grad, l2.weight.grad, l2.loop_weight.grad]
+    for a, b, nm in zip(got, P, ('ent', 'W1', 'L1', 'W2', 'L2')):
+        assert rel_err(a.cpu().numpy(), b.grad.numpy()) < TOL, (preset, nm)
+
+
+# ---- RGCNAggregator.forward / predict_batch / predict vs the unmodified reference -------------------------------------------------
+def _canon(x):
+    x = np.asarray(x, dtype=np.float64)
+    return x[np.lexsort(np.round(x[:, ::-1] * 1e3).T)] if len(x) else x
+
+
+def _ref_setup(fname):
+    from oracle.gen_golden import RENET_SHAPES, det_global_emb, det_params
+    from renet_b200 import synthetic
+    from renet_b200.model import RENet
+    b = load_npz(fname)
+    quads = b['quads'].astype(np.int64)
+    num_e, R, h, nb, seed = (int(b[k]) for k in ('num_e', 'R', 'h', 'nb', 'seed'))
+    m = RENet(num_e, h, R, dropout=0, num_bases=nb)
+    m.load_state_dict(det_params(RENET_SHAPES(num_e, h, R, nb), seed), strict=True)
+    m = m.to(DEV).eval()
+    m.global_emb = det_global_emb(np.unique(quads[:, 3]), h, seed + 1)
+    gd = synthetic.build_graph_dict(quads, R)
+    S, ST, O, OT = synthetic.build_history(quads)
+    return b, m, gd, quads, (S, ST, O, OT), (num_e, R, h, nb)
+
+
+@pytest.mark.parametrize('tag,fname', [('tiny', 'renet_tiny.npz'), ('slice', 'renet_icews18_slice.npz')])
+def test_aggregator_forward_predict_batch_predict_vs_reference(tag, fname):
+    gold = load_npz('aggregator_predict.npz')
+    b, m, gd, quads, (S, ST, O, OT), (num_e, R, h, nb) = _ref_setup(fname)
+    sel = b['sel']
+    batch = torch.from_numpy(quads[sel]).to(DEV)
+    agg = m.aggregator
+    for d, subj in (('subj', True), ('obj', False)):
+        hist = ([S[i] for i in sel], [ST[i] for i in sel]) if subj else ([O[i] for i in sel], [OT[i] for i in sel])
+        rel = m.rel_embeds[:R] if subj else m.rel_embeds[R:]
+        s, r = (batch[:, 0] if subj else batch[:, 2]), batch[:, 1]
+        key = '%s/%s/' % (tag, d)
+        with torch.no_grad():
+            if tag == 'tiny':
+                # forward: every element of both PackedSequences (rows canonicalised inside each time step: tie order)
+                p4, p3 = agg(hist, s, r, m.ent_embeds, rel, gd, m.global_emb, not subj)
+                np.testing.assert_array_equal(p4.batch_sizes.numpy(), gold[key + 'fwd_bs'])
+                for ours, ref in ((p4.data, gold[key + 'fwd_x4']), (p3.data, gold[key + 'fwd_x3'])):
+                    o = 0
+                    for n in gold[key + 'fwd_bs']:
+                        assert rel_err(_canon(ours[o:o + n].cpu().numpy()), _canon(ref[o:o + n])) < TOL
+                        o += int(n)
+                # predict_batch on distinct histories (unsorted twin: order is the caller's, no ties to canonicalise)
+                order = gold[key + 'pb_order'].tolist()
+                hb = ([hist[0][i] for i in order], [hist[1][i] for i in order])
+                q4, q3 = agg.predict_batch(hb, s[order], r[order], m.ent_embeds, rel, gd, m.global_emb, not subj)
+                np.testing.assert_array_equal(q4.batch_sizes.numpy(), gold[key + 'pb_bs'])
+                assert rel_err(q4.data.cpu().numpy(), gold[key + 'pb_x4']) < TOL
+                assert rel_err(q3.data.cpu().numpy(), gold[key + 'pb_x3']) < TOL
+            k = int(gold[key + 'k'])
+            inp, inp_r = agg.predict((hist[0][k], hist[1][k]), s[k], r[k], m.ent_embeds, rel, gd, m.global_emb, not subj)
+            assert inp.shape == gold[key + 'pred_x4'].shape and inp_r.shape == gold[key + 'pred_x3'].shape
+            assert rel_err(inp.cpu().numpy(), gold[key + 'pred_x4']) < TOL
+            assert rel_err(inp_r.cpu().numpy(), gold[key + 'pred_x3']) < TOL
+            # predict_batch the way pred_r_rank2 calls it (model.py:172-191): num_rels copies of one history
+            ss, rr = s[k].repeat(R), torch.arange(R, device=DEV)
+            q4, q3 = agg.predict_batch(([hist[0][k]] * R, [hist[1][k]] * R), ss, rr, m.ent_embeds, rel, gd, m.global_emb,
+                                       not subj)
+            np.testing.assert_array_equal(q4.batch_sizes.numpy(), gold[key + 'rank_bs'])
+            rows = gold[key + 'rank_rows']
+            assert rel_err(q4.data[rows].cpu().numpy(), gold[key + 'rank_x4']) < TOL
+            assert rel_err(q3.data[rows].cpu().numpy(), gold[key + 'rank_x3']) < TOL
+            assert rel_err(q4.data.double().sum(0).cpu().numpy(), gold[key + 'rank_x4_sum']) < TOL

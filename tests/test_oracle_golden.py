@@ -178,3 +178,33 @@ def test_restate_vs_live_reference_random_layers():
         out = restate.rgcn_block_layer(H, layer.weight.detach(), layer.loop_weight.detach(), t(src), t(dst), t(ty),
                                        g.ndata['norm'].view(-1), True, 100)
         assert rel_err(out.numpy(), g.ndata['h'].detach().numpy()) < TOL
+
+
+def _canon(x):
+    """rows in a canonical order (ties among equal history lengths may be ordered differently, model.py:81)"""
+    x = np.asarray(x, dtype=np.float64)
+    return x[np.lexsort(np.round(x[:, ::-1] * 1e3).T)] if len(x) else x
+
+
+def test_restatement_packed_inputs_elementwise_vs_reference_aggregator():
+    """oracle/restate.py's packed GRU inputs, ELEMENT-wise, against RGCNAggregator.forward of the unmodified reference
+    (tests/golden/aggregator_predict.npz, tiny stream)."""
+    from oracle.gen_golden import RENET_SHAPES, det_global_emb, det_params
+    tiny, gold = load_npz('renet_tiny.npz'), load_npz('aggregator_predict.npz')
+    quads = tiny['quads'].astype(np.int64)
+    num_e, R, h, nb, seed = (int(tiny[k]) for k in ('num_e', 'R', 'h', 'nb', 'seed'))
+    P = det_params(RENET_SHAPES(num_e, h, R, nb), seed)
+    glob = det_global_emb(np.unique(quads[:, 3]), h, seed + 1)
+    gd = restate.build_graph_dict(quads, R)
+    S, ST, O, OT = restate.build_history(quads, num_e)
+    sel = tiny['sel']
+    for d, subj, H, HT in (('subj', True, S, ST), ('obj', False, O, OT)):
+        out = restate.renet_forward(P, quads[sel], [H[i] for i in sel], [HT[i] for i in sel], gd, glob, subj, R, nb)
+        perm = out['perm']
+        np.testing.assert_array_equal(out['batch_sizes'], gold['tiny/%s/fwd_bs' % d])
+        for ours, ref in ((out['X4'][perm], gold['tiny/%s/fwd_x4' % d]), (out['X3'][perm], gold['tiny/%s/fwd_x3' % d])):
+            # time-major packing: step t owns rows [sum(bs[:t]), sum(bs[:t+1])); compare step by step, rows canonicalised
+            o = 0
+            for n in out['batch_sizes']:
+                assert rel_err(_canon(ours[o:o + n].numpy()), _canon(ref[o:o + n])) < 2e-6
+                o += int(n)
