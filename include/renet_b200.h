@@ -46,9 +46,6 @@ int64_t renet_launch_count(void);
  * renet_set_gemm_engine returns the previous engine. */
 int renet_set_gemm_engine(int engine);
 int renet_get_gemm_engine(void);
-/* Experiment knob for renet_rgcn_gather's d=200 forward kernel (0 = default; 1, 2, 6, 7 = measured alternatives, see
- * rgcn_fwd.cu); results agree across variants (0, 6, 7 bit for bit).  Returns the previous value. */
-int renet_set_gather_variant(int variant);
 /* Packed-weight cache of the tcgen05 GEMM engine.  The engine consumes weights (self-loop matrices, GRU W_ih / W_hh)
  * in a packed shared-memory operand image; packing is a kernel launch per weight per call.  Declaring a weight
  * generation >= 0 promises that every weight passed by pointer is unchanged while the generation is unchanged: packed
@@ -56,10 +53,6 @@ int renet_set_gather_variant(int variant);
  * them.  generation < 0 (default) disables the cache: weights are packed on every call.  The Python host derives the
  * generation from the parameters' identities and in-place version counters. */
 int renet_set_weight_generation(int64_t generation);
-/* Experiment knob (with renet_set_gather_variant(7)): up to 48 distinct relation-type ids (rows of the [R2, ...] block
- * table, host array) that occur most often on edges; the fused gather then runs as a persistent kernel that keeps those
- * rows in shared memory.  Bit-identical results; measured slower than the default kernel.  n_hot = 0 clears it. */
-int renet_set_hot_relations(const int32_t* hot_rel, int32_t n_hot, int32_t R2);
 /* Optional caller-owned DEVICE scratch buffer (128-byte aligned) the tensor-core GEMM engine uses for the packed
  * (hi/lo split, K-major, 128-byte-swizzled) copy of the B operand, so that GEMM CTAs can fetch it with TMA bulk
  * copies.  Needs ceil(N/200)*ceil(K/32)*53248 bytes per GEMM (W_loop: 373 KB; GRU input projection: 2.2 MB); without
@@ -120,20 +113,6 @@ int renet_rgcn_gather(const float* H, const int32_t* h_index, const float* W,
                       const float* norm, float* Hout,
                       int64_t N, int64_t E, int32_t d_in, int32_t d_out,
                       int32_t num_bases, int32_t R2, int32_t relu, int32_t has_loop, void* stream);
-
-/* Component-resident variant of renet_rgcn_gather for batched graphs whose nodes are grouped by
- * component (dgl.batch of sub-graphs, utils.py:238): comp_ptr [G+1] = node offsets of the components (every
- * edge stays inside one component), comp_order [G] or NULL = launch order (largest first balances the
- * SMs), rel_slot [R2] / hot_rel [n_hot] (n_hot <= 40, may be 0/NULL) = the relation rows to keep in shared
- * memory (rel_slot[r] = i iff hot_rel[i] = r, else -1).  Same result as renet_rgcn_gather; shapes other than
- * d=200/num_bases=100 fall back to it. */
-int renet_rgcn_gather_comp(const float* H, const int32_t* h_index, const float* W,
-                           const int32_t* row_ptr, const int32_t* col_src, const int32_t* col_type,
-                           const float* norm, float* Hout,
-                           const int32_t* comp_ptr, const int32_t* comp_order,
-                           const int32_t* rel_slot, const int32_t* hot_rel, int32_t n_hot,
-                           int64_t N, int64_t E, int64_t G, int32_t d_in, int32_t d_out,
-                           int32_t num_bases, int32_t R2, int32_t relu, int32_t has_loop, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * RGCN block-diagonal layer, backward (autograd of the above; the reference relies on

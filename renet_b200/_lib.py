@@ -20,9 +20,7 @@ SIGNATURES = {
     'renet_launch_count': (_i64, []),
     'renet_set_gemm_engine': (ctypes.c_int, [ctypes.c_int]),
     'renet_get_gemm_engine': (ctypes.c_int, []),
-    'renet_set_gather_variant': (ctypes.c_int, [ctypes.c_int]),
     'renet_set_weight_generation': (ctypes.c_int, [_i64]),
-    'renet_set_hot_relations': (ctypes.c_int, [_vp, _i32, _i32]),
     'renet_set_scratch': (ctypes.c_int, [_vp, _i64]),
     'renet_csr_workspace_bytes': (_i64, [_i64, _i64]),
     'renet_build_csr': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
@@ -30,7 +28,6 @@ SIGNATURES = {
     'renet_selfloop_gemm': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     'renet_selfloop_gemm_bwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     'renet_rgcn_gather': (ctypes.c_int, [_vp] * 8 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
-    'renet_rgcn_gather_comp': (ctypes.c_int, [_vp] * 12 + [_i32, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     'renet_rgcn_block_bwd': (ctypes.c_int, [_vp] * 17 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     'renet_scatter_add_rows': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
     'renet_gru_workspace_bytes': (_i64, [_i64, _i64, _i64, _i32]),

@@ -24,12 +24,6 @@ int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, c
                        const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout,
                        int64_t N, int64_t E, int d_in, int d_out, int nb, int relu, int has_loop,
                        cudaStream_t stream, int R2 = -1);
-int set_hot_relations(const int32_t* hot_rel_host, int n_hot, int R2);
-int launch_rgcn_gather_comp(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
-                            const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout,
-                            const int32_t* comp_ptr, const int32_t* comp_order, const int32_t* rel_slot,
-                            const int32_t* hot_rel, int n_hot, int64_t G, int relu, int has_loop,
-                            cudaStream_t stream);
 int launch_rgcn_bwd(const float* H, const int32_t* h_index, const float* W, const float* Wloop,
                     const int32_t* t_row_ptr, const int32_t* t_col_dst, const int32_t* t_col_type,
                     const int32_t* rel_ptr, const int32_t* rel_src, const int32_t* rel_dst, const float* norm,
@@ -63,8 +57,6 @@ int launch_pack_inputs(const float* H2, const int32_t* readout, const int32_t* r
 int gemm_mode();
 int set_gemm_mode(int m);
 void set_scratch(void* p, int64_t bytes);
-int gather_variant();
-int set_gather_variant(int v);
 
 namespace {
 
@@ -130,9 +122,7 @@ const char* renet_last_error(void) { return g_err; }
 int64_t renet_launch_count(void) { return g_launches.load(); }
 int renet_set_gemm_engine(int engine) { return set_gemm_mode(engine); }
 int renet_get_gemm_engine(void) { return gemm_mode(); }
-int renet_set_gather_variant(int variant) { return set_gather_variant(variant); }
 int renet_set_weight_generation(int64_t generation) { renet::set_weight_generation(generation); return RENET_OK; }
-int renet_set_hot_relations(const int32_t* hot_rel, int32_t n_hot, int32_t R2) { return set_hot_relations(hot_rel, n_hot, R2); }
 int renet_set_scratch(void* device_ptr, int64_t bytes) {
   RENET_CHECK_ARG(bytes >= 0 && (device_ptr != nullptr || bytes == 0), "renet_set_scratch: bad arguments");
   set_scratch(device_ptr, bytes);
@@ -204,27 +194,6 @@ int renet_rgcn_gather(const float* H, const int32_t* h_index, const float* W, co
   RENET_CHECK_ARG(E == 0 || (col_src && col_type), "renet_rgcn_gather: null edge arrays");
   return launch_rgcn_gather(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, N, E, d_in, d_out, num_bases,
                             relu, has_loop, (cudaStream_t)stream, R2);
-}
-
-int renet_rgcn_gather_comp(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
-                           const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout,
-                           const int32_t* comp_ptr, const int32_t* comp_order, const int32_t* rel_slot,
-                           const int32_t* hot_rel, int32_t n_hot, int64_t N, int64_t E, int64_t G, int32_t d_in,
-                           int32_t d_out, int32_t num_bases, int32_t R2, int32_t relu, int32_t has_loop,
-                           void* stream) {
-  int rc = check_layer_args("renet_rgcn_gather_comp", H, W, row_ptr, norm, Hout, N, E, d_in, d_out, num_bases, R2);
-  if (rc) return rc;
-  RENET_CHECK_ARG(E == 0 || (col_src && col_type), "renet_rgcn_gather_comp: null edge arrays");
-  RENET_CHECK_ARG(n_hot >= 0 && n_hot <= 40 && (n_hot == 0 || (rel_slot && hot_rel)),
-                  "renet_rgcn_gather_comp: n_hot must be in [0,40] with rel_slot/hot_rel given");
-  const bool fast = d_in == 200 && d_out == 200 && num_bases == 100 && E > 0 && comp_ptr != nullptr && G > 0 &&
-                    ((reinterpret_cast<uintptr_t>(H) | reinterpret_cast<uintptr_t>(W) |
-                      reinterpret_cast<uintptr_t>(Hout)) & 15) == 0;
-  if (!fast)   // other shapes / graphs without component structure: the tile kernel
-    return launch_rgcn_gather(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, N, E, d_in, d_out, num_bases,
-                              relu, has_loop, (cudaStream_t)stream);
-  return launch_rgcn_gather_comp(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, comp_ptr, comp_order,
-                                 rel_slot, hot_rel, n_hot, G, relu, has_loop, (cudaStream_t)stream);
 }
 
 int renet_rgcn_block_fwd(const float* H, const int32_t* h_index, const float* W, const float* Wloop,

@@ -74,6 +74,9 @@ int sgemm_tn(const float* A, const int32_t* a_index, int64_t lda, const float* B
 int sgemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
              int64_t M, int32_t N, int32_t K, bool accumulate, cudaStream_t stream);
 
+// 0 = automatic, 1 = tile kernels only, 2 = sliced kernels whenever possible (RENET_GATHER_KERNEL=tile|sliced; rgcn_fwd.cu)
+int gather_kernel_choice();
+
 // tcgen05 GEMM engine building blocks (umma_gemm.cu); gemm_mode() == 1 selects the engine
 int gemm_mode();
 int64_t umma_packed_bytes(int N, int K);

@@ -14,8 +14,6 @@ import torch.nn.functional as F
 from . import _lib
 
 
-USE_COMPONENT_KERNEL = False
-
 
 def _buf(shape, like, dtype=torch.float32):
     return torch.empty(shape, dtype=dtype, device=like.device)
@@ -83,23 +81,11 @@ class _GatherFn(torch.autograd.Function):
             if out is loop:
                 ctx.mark_dirty(loop)
         d_in = H.shape[1]
-        comp = getattr(g, 'comp', None)
-        if USE_COMPONENT_KERNEL and comp is not None and g.E > 0 and comp[bool(reverse)][2].numel() <= W.shape[0]:
-            # batched history graph with its component table: component-resident kernel (experimental: slower
-            # than the tile kernel on B200 at ICEWS18 scale)
-            cptr, corder, slot, hot, n_hot = comp[bool(reverse)]
-            rc = L.renet_rgcn_gather_comp(_lib.ptr(H), _lib.ptr(h_index), _lib.ptr(W), _lib.ptr(g.row_ptr),
-                                          _lib.ptr(g.col_src), _lib.ptr(g.col_type(reverse)), _lib.ptr(g.norm),
-                                          _lib.ptr(out), _lib.ptr(cptr), _lib.ptr(corder), _lib.ptr(slot),
-                                          _lib.ptr(hot), n_hot, g.N, g.E, g.G, d_in, d_out, num_bases, W.shape[0],
-                                          int(relu), int(loop is not None), _lib.stream())
-            _lib.check(rc, 'renet_rgcn_gather_comp')
-        else:
-            rc = L.renet_rgcn_gather(_lib.ptr(H), _lib.ptr(h_index), _lib.ptr(W), _lib.ptr(g.row_ptr),
-                                     _lib.ptr(g.col_src), _lib.ptr(g.col_type(reverse)), _lib.ptr(g.norm),
-                                     _lib.ptr(out), g.N, g.E_launch, d_in, d_out, num_bases, W.shape[0], int(relu),
-                                     int(loop is not None), _lib.stream())
-            _lib.check(rc, 'renet_rgcn_gather')
+        rc = L.renet_rgcn_gather(_lib.ptr(H), _lib.ptr(h_index), _lib.ptr(W), _lib.ptr(g.row_ptr),
+                                 _lib.ptr(g.col_src), _lib.ptr(g.col_type(reverse)), _lib.ptr(g.norm),
+                                 _lib.ptr(out), g.N, g.E_launch, d_in, d_out, num_bases, W.shape[0], int(relu),
+                                 int(loop is not None), _lib.stream())
+        _lib.check(rc, 'renet_rgcn_gather')
         ctx.save_for_backward(H, W, out)
         ctx.g, ctx.reverse, ctx.relu, ctx.nb, ctx.h_index, ctx.has_loop = g, reverse, relu, num_bases, h_index, loop is not None
         return out
