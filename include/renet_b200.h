@@ -141,6 +141,19 @@ int renet_rgcn_block_bwd(const float* H, const int32_t* h_index,
                          int64_t N, int64_t E, int32_t d_in, int32_t d_out,
                          int32_t num_bases, int32_t R2, int32_t relu, void* stream);
 
+/* The same backward for a graph whose destinations are a compacted subset of its nodes (the read-out sub-graph of
+ * renet_readout_subgraph): H / dH have N_src rows (sources keep full-graph ids: t_row_ptr [N_src+1] is the CSR by source),
+ * Hout / dHout / norm have N_dst rows (t_col_dst and rel_dst hold compact destination ids).  No self-loop part (the
+ * caller runs renet_selfloop_gemm_bwd over the destination rows).  G_ws: N_dst*d_out (rounded up to 4) floats; on return
+ * it holds P = dHout * act'(Hout). */
+int renet_rgcn_bipartite_bwd(const float* H, const float* W,
+                             const int32_t* t_row_ptr, const int32_t* t_col_dst, const int32_t* t_col_type,
+                             const int32_t* rel_ptr, const int32_t* rel_src, const int32_t* rel_dst,
+                             const float* norm, const float* Hout, const float* dHout,
+                             float* dH, float* dW, float* G_ws,
+                             int64_t N_src, int64_t N_dst, int64_t E, int32_t d_in, int32_t d_out,
+                             int32_t num_bases, int32_t R2, int32_t relu, void* stream);
+
 /* Backward of renet_selfloop_gemm:  dH = dLoop @ Wloop^T  (written),  dWloop += Hin^T @ dLoop.
  * ws: d_in*d_out floats. */
 int renet_selfloop_gemm_bwd(const float* H, const int32_t* h_index, const float* Wloop,
@@ -307,7 +320,9 @@ int renet_prepare_sequences(const int64_t* triplets, int32_t ld, int32_t col_s, 
 /* One call for the whole forward hot path of one direction (inference / no autograd):
  *   H1 = relu-layer(ent[node_ent]), H2 = linear-layer(H1)   (renet_rgcn_block_fwd x2, Aggregator.py:136-137)
  *   hn4, hn3 = renet_gru_fwd(H2, ...)                          (Aggregator.py:139-165 + model.py:86,94)
- * Same arguments as the individual entry points; H1/H2 [N,h] are caller-provided outputs. */
+ * Same arguments as the individual entry points; H1/H2 [N,h] are caller-provided outputs.  With a read-out sub-graph
+ * (sub_* = the outputs of renet_readout_subgraph for this batch and type column; all NULL = none) layer 2 runs on it:
+ * H2 then holds S compact rows and the GRU reads them through sub_readout. */
 int renet_encode_fwd(const float* ent, const int32_t* node_ent, const int32_t* row_ptr, const int32_t* col_src,
                      const int32_t* col_type, const float* norm,
                      const float* W1, const float* Wloop1, const float* W2, const float* Wloop2,
@@ -318,6 +333,8 @@ int renet_encode_fwd(const float* ent, const int32_t* node_ent, const int32_t* r
                      const float* w_ih4, const float* w_hh4, const float* b_ih4, const float* b_hh4,
                      const float* w_ih3, const float* w_hh3, const float* b_ih3, const float* b_hh3,
                      float* hn4, float* hn3, int64_t S, int64_t Q, int64_t T, int32_t h, int32_t num_bases,
+                     const int32_t* sub_uniq, const int32_t* sub_readout, const int32_t* sub_row_ptr,
+                     const int32_t* sub_col_src, const int32_t* sub_col_type, const float* sub_norm,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Materialise the packed GRU inputs exactly as the reference's aggregator returns them
@@ -328,6 +345,25 @@ int renet_pack_inputs(const float* H2, const int32_t* readout, const int32_t* ro
                       const int32_t* row_seq, const int32_t* seq_s, const int32_t* seq_r,
                       const int32_t* packed_row, float* X4, float* X3,
                       int64_t S, int32_t h, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Read-out sub-graph.  The reference runs layer 2 of the aggregator on every node of the batched graph and then keeps the
+ * read-out rows only (Aggregator.py:139-140: embeds_mean[node_ids_graph], 26 % of the rows at ICEWS18 scale).  Layer 2 at a
+ * read-out node depends on layer 1 at its in-neighbours only, so layer 2 over the sub-graph {edges whose destination is a
+ * read-out node} is identical on every consumed row (optimisation (i)).  Built on the device, no
+ * host round trip; launches are sized by the capacities, the actual sizes come back in counts:
+ *   readout [S] -> uniq [S] (distinct read-out nodes ascending = compact destination -> node; unused tail = 0),
+ *   readout_c [S] (read-out row -> compact destination), row_ptr2 [S+1] (CSR by compact destination; unused
+ *   destinations have no edges), col_src2 / col_type2 (capacity of col_src; sources keep full-graph ids), norm2 [S]
+ *   (tail 1), counts [2] = {U, E2}.
+ * Layer 2 is then renet_selfloop_gemm(H1, uniq, ...) + renet_rgcn_gather(H1, NULL, W2, row_ptr2, col_src2, col_type2,
+ * norm2, H2c, S, ...) and the GRU reads H2c through readout_c.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t renet_readout_subgraph_workspace_bytes(int64_t N, int64_t S);
+int renet_readout_subgraph(const int32_t* readout, int64_t S, int64_t N,
+                           const int32_t* row_ptr, const int32_t* col_src, const int32_t* col_type, const float* norm,
+                           int32_t* uniq, int32_t* readout_c, int32_t* row_ptr2, int32_t* col_src2, int32_t* col_type2,
+                           float* norm2, int32_t* counts, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Optimiser step of the reference training loop on FLAT fp32 buffers (reference train.py:140-142:

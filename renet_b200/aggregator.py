@@ -23,19 +23,20 @@ class _PackInputsFn(torch.autograd.Function):
     """X4/X3 in packed (time-major) order, Aggregator.py:139-165 without the Python loop."""
 
     @staticmethod
-    def forward(ctx, H2, ent, rel, glob, hb, seq_s, seq_r):
+    def forward(ctx, H2, ent, rel, glob, hb, seq_s, seq_r, readout=None):
         L = _lib.lib()
+        readout = hb.readout if readout is None else readout
         _lib.require_cuda(H2, ent, rel, glob)
         H2, ent, rel, glob = H2.contiguous(), ent.contiguous(), rel.contiguous(), glob.contiguous()
         h = H2.shape[1]
         X4 = torch.empty(hb.S, 4 * h, device=H2.device)
         X3 = torch.empty(hb.S, 3 * h, device=H2.device)
-        rc = L.renet_pack_inputs(_lib.ptr(H2), _lib.ptr(hb.readout), _lib.ptr(hb.row_glob), _lib.ptr(glob),
+        rc = L.renet_pack_inputs(_lib.ptr(H2), _lib.ptr(readout), _lib.ptr(hb.row_glob), _lib.ptr(glob),
                                  _lib.ptr(ent), _lib.ptr(rel), _lib.ptr(hb.row_seq), _lib.ptr(seq_s),
                                  _lib.ptr(seq_r), _lib.ptr(hb.packed_row), _lib.ptr(X4), _lib.ptr(X3), hb.S, h,
                                  _lib.stream())
         _lib.check(rc, 'renet_pack_inputs')
-        ctx.hb, ctx.seq_s, ctx.seq_r = hb, seq_s, seq_r
+        ctx.hb, ctx.seq_s, ctx.seq_r, ctx.readout = hb, seq_s, seq_r, readout
         ctx.shapes = (H2.shape, ent.shape, rel.shape, glob.shape)
         return X4, X3
 
@@ -45,11 +46,11 @@ class _PackInputsFn(torch.autograd.Function):
         row = hb.packed_row.long()
         q = hb.row_seq.long()[row]
         dev = dX4.device
-        dH2 = torch.zeros(ctx.shapes[0], device=dev).index_add_(0, hb.readout.long()[row], dX4[:, :h] + dX3[:, :h])
+        dH2 = torch.zeros(ctx.shapes[0], device=dev).index_add_(0, ctx.readout.long()[row], dX4[:, :h] + dX3[:, :h])
         dent = torch.zeros(ctx.shapes[1], device=dev).index_add_(0, ctx.seq_s.long()[q], dX4[:, h:2 * h] + dX3[:, h:2 * h])
         drel = torch.zeros(ctx.shapes[2], device=dev).index_add_(0, ctx.seq_r.long()[q], dX4[:, 2 * h:3 * h])
         dglob = torch.zeros(ctx.shapes[3], device=dev).index_add_(0, hb.row_glob.long()[row], dX4[:, 3 * h:] + dX3[:, 2 * h:])
-        return dH2, dent, drel, dglob, None, None, None
+        return dH2, dent, drel, dglob, None, None, None, None
 
 
 class RGCNAggregator(nn.Module):
@@ -96,11 +97,14 @@ class RGCNAggregator(nn.Module):
         return assemble_history_batch(s_hist[0], s_hist[1], s_host, graph_dict, device, sort=sort)
 
     def aggregate(self, hb, ent_embeds, reverse):
-        """The two RGCN layers over the batched history graph (Aggregator.py:136-139); the embedding
-        lookup ndata['h'] = ent_embeds[id] (utils.py:239) is fused into layer 1."""
+        """The two RGCN layers over the batched history graph (Aggregator.py:136-139); the embedding lookup
+        ndata['h'] = ent_embeds[id] (utils.py:239) is fused into layer 1.  Layer 2 runs on the read-out sub-graph only
+        (Aggregator.py:140 keeps nothing but the read-out rows of its output): returns (H2c [S_cap, h], readout_c) with
+        H2c[readout_c[i]] == the reference's embeds_mean[node_ids_graph][i]."""
         g = hb.graph
         H1 = self.rgcn1.apply_layer(g, ent_embeds, g.node_ent, reverse)
-        return self.rgcn2.apply_layer(g, H1, None, reverse)
+        sub = g.readout_sub(hb.readout, reverse)
+        return self.rgcn2.apply_layer(sub, H1, None, reverse, loop_index=sub.uniq), sub.readout_c
 
     def _sorted_ids(self, hb, s, r, device):
         idx = hb.sample_order(device)
@@ -111,10 +115,10 @@ class RGCNAggregator(nn.Module):
     def _packed(self, s_hist, s, r, ent_embeds, rel_embeds, graph_dict, global_emb, reverse, sort):
         dev = ent_embeds.device
         hb = self._batch(s_hist, s, graph_dict, dev, sort)
-        H2 = self.aggregate(hb, ent_embeds, reverse)
+        H2, readout = self.aggregate(hb, ent_embeds, reverse)
         glob = global_rows(global_emb, hb.times, self.h_dim, dev)
         _, _, seq_s, seq_r = self._sorted_ids(hb, s, r, dev)
-        X4, X3 = _PackInputsFn.apply(H2, ent_embeds, rel_embeds, glob, hb, seq_s, seq_r)
+        X4, X3 = _PackInputsFn.apply(H2, ent_embeds, rel_embeds, glob, hb, seq_s, seq_r, readout)
         X4, X3 = self.dropout(X4), self.dropout(X3)                       # Aggregator.py:157-158
         bs = torch.from_numpy(hb.batch_sizes.astype(np.int64))
         return PackedSequence(X4, bs), PackedSequence(X3, bs), hb
@@ -150,10 +154,10 @@ class RGCNAggregator(nn.Module):
         with _lib.weight_generation(self._pack_token, weights):
             if not torch.is_grad_enabled() and not self.training:
                 return self._encode_inference(hb, s, r, ent_embeds, rel_embeds, global_emb, reverse, encoder, encoder_r, triplets)
-            H2 = self.aggregate(hb, ent_embeds, reverse)
+            H2, readout = self.aggregate(hb, ent_embeds, reverse)
             glob = global_rows_of_batch(global_emb, hb, self.h_dim, dev)
             _, _, seq_s, seq_r = self._sorted_ids(hb, s, r, dev)
-            s_h, s_q = fused_gru(H2, ent_embeds, rel_embeds, glob, hb, seq_s, seq_r, encoder, encoder_r)
+            s_h, s_q = fused_gru(H2, ent_embeds, rel_embeds, glob, hb, seq_s, seq_r, encoder, encoder_r, readout=readout)
             return s_h, s_q, hb
 
     def _encode_inference(self, hb, s, r, ent_embeds, rel_embeds, global_emb, reverse, encoder, encoder_r, triplets=None):
@@ -189,18 +193,20 @@ class RGCNAggregator(nn.Module):
         p4, p3 = _gru_params(encoder), _gru_params(encoder_r)
         rel = rel_embeds.contiguous()
         T = glob.shape[0]
-        H = torch.empty(2, g.N, h, device=dev)
+        sub = g.readout_sub(hb.readout, reverse)       # layer 2 runs on the read-out sub-graph (Aggregator.py:140)
+        H = torch.empty(g.N + hb.S, h, device=dev)     # H1 [N] | H2 compact [S]
         hn = torch.zeros(2, B, h, device=dev)          # rows >= Q stay zero: samples without history
         nbytes = int(L.renet_gru_workspace_bytes(hb.S, Q, T, h))
         ws = torch.empty(nbytes // 4 + 4, dtype=torch.float32, device=dev)
         bs = hb.batch_sizes
         l1, l2 = self.rgcn1, self.rgcn2
         rc = L.renet_encode_fwd(P(ent_embeds), P(g.node_ent), P(g.row_ptr), P(g.col_src), P(g.col_type(reverse)),
-                                P(g.norm), P(l1.weight), P(l1.loop_weight), P(l2.weight), P(l2.loop_weight), P(H[0]),
-                                P(H[1]), g.N, g.E_launch, l1.weight.shape[0], P(hb.readout), P(row_glob), P(glob), P(rel),
+                                P(g.norm), P(l1.weight), P(l1.loop_weight), P(l2.weight), P(l2.loop_weight), P(H),
+                                P(H[g.N:]), g.N, g.E_launch, l1.weight.shape[0], P(hb.readout), P(row_glob), P(glob), P(rel),
                                 P(seq_s), P(seq_r), P(g.seq_len_dev), P(hb.seq_start),
                                 bs.ctypes.data_as(_lib.ctypes.c_void_p), len(bs), P(p4[0]), P(p4[1]), P(p4[2]), P(p4[3]),
                                 P(p3[0]), P(p3[1]), P(p3[2]), P(p3[3]), P(hn[0]), P(hn[1]), hb.S, Q, T, h, l1.num_bases,
-                                P(ws), nbytes, _lib.stream())
+                                P(sub.uniq), P(sub.readout_c), P(sub.row_ptr), P(sub.col_src), P(sub.col_type(reverse)),
+                                P(sub.norm), P(ws), nbytes, _lib.stream())
         _lib.check(rc, 'renet_encode_fwd')
         return hn[0], hn[1], hb

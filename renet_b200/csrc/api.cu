@@ -28,7 +28,8 @@ int launch_rgcn_bwd(const float* H, const int32_t* h_index, const float* W, cons
                     const int32_t* t_row_ptr, const int32_t* t_col_dst, const int32_t* t_col_type,
                     const int32_t* rel_ptr, const int32_t* rel_src, const int32_t* rel_dst, const float* norm,
                     const float* Hout, const float* dHout, float* dH, float* dW, float* dWloop, float* G_ws,
-                    int64_t N, int64_t E, int d_in, int d_out, int nb, int R2, int relu, cudaStream_t stream);
+                    int64_t N, int64_t E, int d_in, int d_out, int nb, int R2, int relu, cudaStream_t stream,
+                    int64_t N_dst = -1);
 int launch_selfloop_bwd(const float* H, const int32_t* h_index, const float* Wloop, const float* dLoop, float* dH,
                         float* dWloop, float* WloopT_ws, int64_t N, int d_in, int d_out, cudaStream_t stream);
 int launch_scatter_add_rows(const float* src, const int32_t* index, float* dst, int64_t n_rows, int d,
@@ -230,6 +231,26 @@ int renet_rgcn_block_bwd(const float* H, const int32_t* h_index, const float* W,
                          (cudaStream_t)stream);
 }
 
+int renet_rgcn_bipartite_bwd(const float* H, const float* W, const int32_t* t_row_ptr, const int32_t* t_col_dst,
+                             const int32_t* t_col_type, const int32_t* rel_ptr, const int32_t* rel_src, const int32_t* rel_dst,
+                             const float* norm, const float* Hout, const float* dHout, float* dH, float* dW, float* G_ws,
+                             int64_t N_src, int64_t N_dst, int64_t E, int32_t d_in, int32_t d_out, int32_t num_bases, int32_t R2,
+                             int32_t relu, void* stream) {
+  int rc = check_layer_args("renet_rgcn_bipartite_bwd", H, W, t_row_ptr, norm, dHout, N_src, E, d_in, d_out, num_bases, R2);
+  if (rc) return rc;
+  RENET_CHECK_ARG(N_dst >= 0 && N_dst < (int64_t(1) << 31), "renet_rgcn_bipartite_bwd: bad N_dst");
+  RENET_CHECK_ARG(dH && dW && G_ws, "renet_rgcn_bipartite_bwd: null output");
+  RENET_CHECK_ARG(!relu || Hout != nullptr, "renet_rgcn_bipartite_bwd: relu backward needs Hout");
+  if (N_src == 0) return RENET_OK;
+  if (E == 0 || N_dst == 0) {       // no edge reaches a destination: dH = 0, dW unchanged
+    RENET_CHECK_CUDA(cudaMemsetAsync(dH, 0, (size_t)N_src * d_in * sizeof(float), (cudaStream_t)stream));
+    return RENET_OK;
+  }
+  RENET_CHECK_ARG(t_col_dst && t_col_type && rel_ptr && rel_src && rel_dst, "renet_rgcn_bipartite_bwd: null edge arrays");
+  return launch_rgcn_bwd(H, nullptr, W, nullptr, t_row_ptr, t_col_dst, t_col_type, rel_ptr, rel_src, rel_dst, norm, Hout, dHout,
+                         dH, dW, nullptr, G_ws, N_src, E, d_in, d_out, num_bases, R2, relu, (cudaStream_t)stream, N_dst);
+}
+
 int renet_selfloop_gemm_bwd(const float* H, const int32_t* h_index, const float* Wloop, const float* dLoop,
                             float* dH, float* dWloop, float* ws, int64_t N, int32_t d_in, int32_t d_out,
                             void* stream) {
@@ -307,14 +328,32 @@ int renet_encode_fwd(const float* ent, const int32_t* node_ent, const int32_t* r
                      const int32_t* host_batch_sizes, int32_t max_len, const float* w_ih4, const float* w_hh4,
                      const float* b_ih4, const float* b_hh4, const float* w_ih3, const float* w_hh3, const float* b_ih3,
                      const float* b_hh3, float* hn4, float* hn3, int64_t S, int64_t Q, int64_t T, int32_t h,
-                     int32_t num_bases, void* workspace, int64_t workspace_bytes, void* stream) {
+                     int32_t num_bases, const int32_t* sub_uniq, const int32_t* sub_readout, const int32_t* sub_row_ptr,
+                     const int32_t* sub_col_src, const int32_t* sub_col_type, const float* sub_norm, void* workspace,
+                     int64_t workspace_bytes, void* stream) {
   // layer 1 (embedding lookup fused through node_ent, ReLU), layer 2 (linear), then read-out + both GRUs
   int rc = renet_rgcn_block_fwd(ent, node_ent, W1, Wloop1, row_ptr, col_src, col_type, norm, H1, N, E, h, h, num_bases, R2,
                                 1, stream);
   if (rc) return rc;
-  rc = renet_rgcn_block_fwd(H1, nullptr, W2, Wloop2, row_ptr, col_src, col_type, norm, H2, N, E, h, h, num_bases, R2, 0,
-                            stream);
-  if (rc) return rc;
+  if (sub_uniq != nullptr) {
+    // layer 2 on the read-out sub-graph (renet_readout_subgraph): S compact destinations, sources = rows of H1
+    RENET_CHECK_ARG(sub_readout && sub_row_ptr && sub_col_src && sub_col_type && sub_norm,
+                    "renet_encode_fwd: incomplete read-out sub-graph");
+    if (S > 0) {
+      if (Wloop2 != nullptr) {
+        rc = sgemm_nn(H1, sub_uniq, h, Wloop2, h, H2, h, nullptr, S, h, h, false, (cudaStream_t)stream);
+        if (rc) return rc;
+      }
+      rc = launch_rgcn_gather(H1, nullptr, W2, sub_row_ptr, sub_col_src, sub_col_type, sub_norm, H2, S, E > 0 ? E : 1, h, h,
+                              num_bases, 0, Wloop2 != nullptr, (cudaStream_t)stream, R2);
+      if (rc) return rc;
+    }
+    readout = sub_readout;
+  } else {
+    rc = renet_rgcn_block_fwd(H1, nullptr, W2, Wloop2, row_ptr, col_src, col_type, norm, H2, N, E, h, h, num_bases, R2, 0,
+                              stream);
+    if (rc) return rc;
+  }
   return renet_gru_fwd(H2, readout, row_glob, glob, ent, rel, seq_s, seq_r, seq_len, seq_start, host_batch_sizes, max_len,
                        w_ih4, w_hh4, b_ih4, b_hh4, w_ih3, w_hh3, b_ih3, b_hh3, hn4, hn3, S, Q, T, h, workspace,
                        workspace_bytes, stream);

@@ -306,13 +306,21 @@ __global__ void gru_gate_bwd_kernel(const float* __restrict__ GI, const float* _
                                     const int32_t* __restrict__ seq_start, const float* __restrict__ Hprev,
                                     const float* __restrict__ dHcur, const float* __restrict__ dhn4,
                                     const float* __restrict__ dhn3, float* __restrict__ dGI,
-                                    float* __restrict__ dGH, float* __restrict__ dHprev, int n_act, int n_next,
-                                    int h, int t) {
+                                    float* __restrict__ dGH, float* __restrict__ dHprev, float* __restrict__ Hprev_zero,
+                                    int Q, int n_act, int n_next, int h, int t) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int per_q = 2 * h;
-  if (i >= n_act * per_q) return;
+  if (i >= Q * per_q) return;
   const int q = i / per_q, c = i % per_q;
   const int enc = c / h, u = c % h;
+  if (q >= n_act) {
+    // sequence already over at step t: its rows of this step's dGH (and of the saved state feeding the batched dW_hh
+    // GEMM, whose workspace rows were never written for it) must be exact zeros
+    float* z = dGH + (int64_t)q * 6 * h + enc * 3 * h + u;
+    z[0] = 0.f; z[h] = 0.f; z[2 * h] = 0.f;
+    if (Hprev_zero != nullptr) Hprev_zero[(int64_t)q * per_q + c] = 0.f;
+    return;
+  }
   const int64_t row = (int64_t)seq_start[q] + t;
   const int64_t g = (int64_t)row_glob[row];
   const int base = enc * 3 * h + u;
@@ -389,7 +397,8 @@ __global__ void unpack_transpose_add_kernel(const float* __restrict__ src, int l
 }
 
 struct GruBwdWs {
-  float *dGI, *dGH, *dPQ, *dPT, *dHa, *dHb, *dBrow, *dBent, *dBrel, *dBglob, *dWhh, *dRows, *dQ, *dbias;
+  float *dGI, *dGH, *dPQ, *dPT, *dHa, *dHb, *dBrow, *dBent, *dBrel, *dBglob, *dWhh, *dRows, *dQ, *dbias, *P_hhT;
+  int64_t p_hht_bytes;
   int64_t total_floats;
 };
 
@@ -398,7 +407,7 @@ GruBwdWs carve_bwd(float* base, int64_t S, int64_t Q, int64_t T, int h) {
   int64_t off = 0;
   auto take = [&](int64_t n) { float* p = base ? base + off : nullptr; off += align4(n); return p; };
   w.dGI = take(S * 6 * h);
-  w.dGH = take(Q * 6 * h);
+  w.dGH = take((int64_t)kMaxLenWs * Q * 6 * h);          // every step's recurrent-gate gradients (one dW_hh GEMM over all steps)
   w.dPQ = take(Q * 6 * h);
   w.dPT = take(T * 6 * h);
   w.dHa = take(Q * 2 * h);
@@ -411,6 +420,9 @@ GruBwdWs carve_bwd(float* base, int64_t S, int64_t Q, int64_t T, int h) {
   w.dRows = take(S * h);
   w.dQ = take(Q * h);
   w.dbias = take(12 * h);
+  off = (off + 31) & ~int64_t(31);                       // 128-byte alignment for the TMA source blocks
+  w.p_hht_bytes = umma_packed_bytes(h, 3 * h);
+  w.P_hhT = take(2 * w.p_hht_bytes / 4);
   w.total_floats = off;
   return w;
 }
@@ -441,35 +453,57 @@ int launch_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_g
   RENET_CHECK_CUDA(cudaMemsetAsync(dH2, 0, N * h * sizeof(float), stream));
   int last = 0;
   while (last < max_len && host_batch_sizes[last] > 0) ++last;
+  if (last > kMaxLenWs) {
+    set_error("renet_gru_bwd: max_len %d exceeds the supported %d", last, kMaxLenWs);
+    return RENET_ERR_INVALID_ARG;
+  }
   const int64_t hs_stride = Q * 2 * h;
+  const int64_t gh_stride = Q * 6 * h;
+  // tensor-core engine: W_hh of both encoders packed ONCE as the B operand of dHprev += dGH @ W_hh (B[k][n] = w_hh[k*h + n])
+  const bool use_umma = gemm_mode() == 1 && umma_shape_ok(h, 3 * h) && (reinterpret_cast<uintptr_t>(b.P_hhT) & 127) == 0;
+  if (use_umma && last > 1) {
+    if ((rc = umma_pack_b(w_hh4, h, 1, h, 3 * h, b.P_hhT, 0, stream))) return rc;
+    if ((rc = umma_pack_b(w_hh3, h, 1, h, 3 * h, reinterpret_cast<uint8_t*>(b.P_hhT) + b.p_hht_bytes, 0, stream))) return rc;
+  }
   float* dHcur = b.dHa;
   float* dHprev = b.dHb;
   for (int t = last - 1; t >= 0; --t) {
     const int n_act = host_batch_sizes[t];
     const int n_next = (t + 1 < last) ? host_batch_sizes[t + 1] : 0;
-    const float* Hprev = (t == 0) ? nullptr : f.Hs + (int64_t)t * hs_stride;
-    const float* GH = f.GH + (int64_t)t * Q * 6 * h;
-    const int total = n_act * 2 * h;
-    gru_gate_bwd_kernel<<<(total + 255) / 256, 256, 0, stream>>>(f.GI, f.PQ, f.PT, GH, f.bhh, row_glob, seq_start,
-                                                                Hprev, dHcur, dhn4, dhn3, b.dGI, b.dGH, dHprev,
-                                                                n_act, n_next, h, t);
+    float* Hprev = (t == 0) ? nullptr : f.Hs + (int64_t)t * hs_stride;
+    const float* GH = f.GH + (int64_t)t * gh_stride;
+    float* dGHt = b.dGH + (int64_t)t * gh_stride;
+    const int64_t total = Q * 2 * h;
+    gru_gate_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(f.GI, f.PQ, f.PT, GH, f.bhh, row_glob, seq_start,
+                                                                            Hprev, dHcur, dhn4, dhn3, b.dGI, dGHt, dHprev, Hprev,
+                                                                            (int)Q, n_act, n_next, h, t);
     RENET_CHECK_LAUNCH("gru_gate_bwd_kernel");
-    // db_hh += colsum(dGH[0:n_act])
-    {
-      const int rpb = 64;
-      dim3 grid((6 * h + 127) / 128, (n_act + rpb - 1) / rpb);
-      colsum_accum_kernel<<<grid, 128, 0, stream>>>(b.dGH, 6 * h, n_act, 6 * h, b.dbias + 6 * h, rpb);
-      RENET_CHECK_LAUNCH("colsum_accum_kernel");
-    }
     if (t > 0) {
-      // dHprev += dGH_enc @ w_hh_enc   ([n,3h] @ [3h,h])
-      if ((rc = sgemm_nn(b.dGH, nullptr, 6 * h, w_hh4, h, dHprev, 2 * h, nullptr, n_act, h, 3 * h, true, stream))) return rc;
-      if ((rc = sgemm_nn(b.dGH + 3 * h, nullptr, 6 * h, w_hh3, h, dHprev + h, 2 * h, nullptr, n_act, h, 3 * h, true, stream))) return rc;
-      // dWhh[k, o] += Hprev[:, k]^T dGH[:, o]   (packed [h, 6h] like Whh)
-      if ((rc = sgemm_tn(Hprev, nullptr, 2 * h, b.dGH, 6 * h, b.dWhh, 6 * h, h, 3 * h, n_act, true, stream))) return rc;
-      if ((rc = sgemm_tn(Hprev + h, nullptr, 2 * h, b.dGH + 3 * h, 6 * h, b.dWhh + 3 * h, 6 * h, h, 3 * h, n_act, true, stream))) return rc;
+      // dHprev += dGH_enc @ w_hh_enc   ([n,3h] @ [3h,h]), both encoders in one launch
+      if (use_umma) {
+        if ((rc = umma_gemm_prepacked(dGHt, nullptr, 6 * h, b.P_hhT, dHprev, 2 * h, nullptr, n_act, h, 3 * h, true, 2, 3 * h,
+                                      b.p_hht_bytes, h, stream)))
+          return rc;
+      } else {
+        if ((rc = sgemm_nn(dGHt, nullptr, 6 * h, w_hh4, h, dHprev, 2 * h, nullptr, n_act, h, 3 * h, true, stream))) return rc;
+        if ((rc = sgemm_nn(dGHt + 3 * h, nullptr, 6 * h, w_hh3, h, dHprev + h, 2 * h, nullptr, n_act, h, 3 * h, true, stream))) return rc;
+      }
     }
     float* tmp = dHcur; dHcur = dHprev; dHprev = tmp;
+  }
+  if (last > 0) {
+    // db_hh += colsum(dGH) over every step (rows of finished sequences are zeros)
+    const int rpb = 256;
+    const int64_t rows = (int64_t)last * Q;
+    dim3 grid((6 * h + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
+    colsum_accum_kernel<<<grid, 128, 0, stream>>>(b.dGH, 6 * h, rows, 6 * h, b.dbias + 6 * h, rpb);
+    RENET_CHECK_LAUNCH("colsum_accum_kernel");
+  }
+  if (last > 1) {
+    // dWhh[k, o] += sum over steps t >= 1 of Hprev_t[:, k]^T dGH_t[:, o]: ONE K-long reduction per encoder over all steps
+    const int64_t K = (int64_t)(last - 1) * Q;
+    if ((rc = sgemm_tn(f.Hs + hs_stride, nullptr, 2 * h, b.dGH + gh_stride, 6 * h, b.dWhh, 6 * h, h, 3 * h, K, true, stream))) return rc;
+    if ((rc = sgemm_tn(f.Hs + hs_stride + h, nullptr, 2 * h, b.dGH + gh_stride + 3 * h, 6 * h, b.dWhh + 3 * h, 6 * h, h, 3 * h, K, true, stream))) return rc;
   }
   // ---- biases of the input projection: every row carries b_ih once ------------------------------------
   {

@@ -252,10 +252,14 @@ int launch_rgcn_bwd(const float* H, const int32_t* h_index, const float* W, cons
                     const int32_t* t_row_ptr, const int32_t* t_col_dst, const int32_t* t_col_type,
                     const int32_t* rel_ptr, const int32_t* rel_src, const int32_t* rel_dst, const float* norm,
                     const float* Hout, const float* dHout, float* dH, float* dW, float* dWloop, float* G_ws,
-                    int64_t N, int64_t E, int d_in, int d_out, int nb, int R2, int relu, cudaStream_t stream) {
+                    int64_t N, int64_t E, int d_in, int d_out, int nb, int R2, int relu, cudaStream_t stream,
+                    int64_t N_dst) {
+  // N = rows of H / dH (sources); N_dst = rows of Hout / dHout / norm (destinations): equal except for the read-out
+  // sub-graph (readout_subgraph.cu), whose destinations are a compacted subset
+  if (N_dst < 0) N_dst = N;
   float* P = G_ws;
-  float* WloopT = G_ws + ((N * d_out + 3) & ~int64_t(3));
-  const int64_t n = N * d_out;
+  float* WloopT = G_ws + ((N_dst * d_out + 3) & ~int64_t(3));
+  const int64_t n = N_dst * d_out;
   const bool al = ((reinterpret_cast<uintptr_t>(dHout) | reinterpret_cast<uintptr_t>(Hout) |
                     reinterpret_cast<uintptr_t>(P)) & 15) == 0;
   if (n % 4 == 0 && al) {
@@ -273,7 +277,7 @@ int launch_rgcn_bwd(const float* H, const int32_t* h_index, const float* W, cons
                     ((reinterpret_cast<uintptr_t>(H) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(dH) |
                       reinterpret_cast<uintptr_t>(dW) | reinterpret_cast<uintptr_t>(P)) & 15) == 0;
   if (fast) {
-    if (R2 <= kSlMaxR2 && gather_kernel_choice() != 1 && (gather_kernel_choice() == 2 || E >= 16384)) {
+    if (R2 <= kSlMaxR2 && gather_kernel_choice() == 2) {
       // batch scale: the sliced persistent kernel on the reversed graph (transposed blocks, per-edge scale norm[dst]):
       // relation rows from shared memory, no atomics, bitwise reproducible dH
       static bool attr_done = false;

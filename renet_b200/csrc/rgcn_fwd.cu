@@ -100,9 +100,11 @@ __global__ void rgcn_gather_generic_kernel(const float* __restrict__ H, const in
 
 }  // namespace
 
-// Which kernel serves the d=200 shape: 0 = automatic (sliced kernel at batch scale, tile kernel for small graphs),
-// 1 = always the tile kernel, 2 = the sliced kernel whenever its shared memory allows.  RENET_GATHER_KERNEL=tile|sliced
-// forces one for A/B measurements (tools/bench_gather.py); results agree to fp32 summation order.
+// Which kernel serves the d=200 shape: 0 = default (the tile kernel), 1 = tile, 2 = the sliced kernel whenever its shared
+// memory allows.  RENET_GATHER_KERNEL=tile|sliced picks one per process for A/B measurements (tools/bench_gather.py); results
+// agree to fp32 summation order.  Measured on B200 at ICEWS18 scale: tile 49 us, sliced 82-98 us -- the
+// sliced kernel moves 20 % fewer bytes through L2 but at 16 warps/SM and ~40 instructions per 3 edge-slices it is issue-bound,
+// so it stays opt-in.
 int gather_kernel_choice() {
   static int v = -1;
   if (v < 0) {
@@ -144,7 +146,7 @@ int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, c
   if (fast) {
     const int choice = gather_kernel_choice();
     // E may be an upper bound (device-assembled batches pass the capacity): the sliced kernel reads row_ptr[N] itself
-    const bool sliced = !passthrough && R2 > 0 && R2 <= kSlMaxR2 && choice != 1 && (choice == 2 || E >= 16384);
+    const bool sliced = !passthrough && R2 > 0 && R2 <= kSlMaxR2 && choice == 2;
     const int key = (relu ? 4 : 0) | (has_loop ? 2 : 0) | (h_index ? 1 : 0);
     if (sliced) {
 #define RENET_LAUNCH_SLICED(R, L, I) return launch_sliced<R, L, I>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, R2, stream)

@@ -6,18 +6,22 @@
 // slices' limit, not HBM's.  The relation table (R2 x 400 floats = 819 KB) does not fit in shared memory, but ONE FIFTH
 // of its columns does: 20 of the 100 blocks x R2 = 512 relations = 160 KB.  So the feature dimension is cut into 5 slices
 // of 40 floats (5 full 32-byte sectors of every 800-byte row) and each persistent CTA (one per SM) works on ONE slice:
-//   * its slice of the whole relation table is staged ONCE into shared memory by TMA (cp.async.bulk.tensor.2d through a
-//     tensor map over W [R2, 400]: boxes of 32 relations x 80 floats, completing on an mbarrier -- 512 one-row bulk copies
-//     were measured first and cost more than the edge walk), and every per-edge weight read is an LDS;
+//   * its slice of the whole relation table is staged ONCE into shared memory by TMA (cp.async.bulk.tensor.4d through a
+//     tensor map that views W [R2, 400] as [R2][50 block pairs][2][4 floats]: a box of 32 relations x 10 pairs x one
+//     parity lands as a dense plane, so the even and the odd blocks of a pair sit in two planes and both per-edge weight
+//     reads are conflict-free LDS.128), completing on an mbarrier;
 //   * per edge and slice only 160 bytes of the source row cross L2->SM (one LDG.128 per lane of a 10-lane group), so
 //     the traffic is E*800 + N*1600 + indices -- what the roofline formula counts;
 //   * a warp = 3 groups of 10 lanes; a warp owns a contiguous, node-aligned range of destinations whose weight
 //     (edges + 2 per node) is 1/(#warps of the slice) of the graph (found by a 16-ary warp search in row_ptr during the
 //     TMA staging), and the three groups split the warp's EDGE range evenly, so heavy destinations never idle lanes;
-//   * each group walks its edges with 8 row loads in flight (double-buffered blocks), keeps the running destination's
-//     sum in registers (edges are destination-sorted: a segmented reduction) and applies norm / self-loop / ReLU when
-//     the destination changes; the self-loop row, norm and next row_ptr entry of the coming destinations arrive
-//     through a 5-deep cp.async ring, so the flush never waits on global memory;
+//   * each group walks its edges with 8 row loads in flight (double-buffered blocks) and keeps the running destination's
+//     sum in registers (edges are destination-sorted: a segmented reduction); when the destination changes the sum goes
+//     to a small per-group buffer in shared memory (12 instructions, no global access: the next row_ptr entries ride in
+//     a register window filled 10 destinations ahead), and at the end of every block the whole warp drains the buffers
+//     together -- self-loop row and norm loads batched, norm / self-loop / ReLU, 160-byte coalesced stores.  (The first
+//     version finished each destination inside the divergent flush through a cp.async ring: 100 instructions at 10
+//     active lanes, 17 M of the kernel's 33 M warp instructions and 137 KB of unrolled code.)
 //   * a destination cut by a group boundary is summed in group order from registers + per-warp head slots: no atomics
 //     of any kind, the result is bitwise reproducible.
 // The same body is the backward dH kernel (BWD: reversed CSR, transposed blocks, per-edge scale norm[dst]).
@@ -34,20 +38,22 @@ constexpr int kSlices = 5;
 constexpr int kSlWarps = 16;
 constexpr int kSlThreads = kSlWarps * 32;
 constexpr int kSlKB = 8;             // edges per index block (row loads in flight per group: one block)
-constexpr int kSlRing = 5;           // prefetch depth of the per-destination epilogue inputs
-constexpr int kSlRingWords = 44;     // 40 self-loop floats + norm + next row_ptr + pad (176 B)
-constexpr int kSlNodeCost = 2;       // a destination costs about two edges (ring prefetch + flush)
-constexpr int kSlBoxRows = 32;      // relations per TMA box
+constexpr int kSlDone = 4;           // finished destinations a group buffers before the warp drains them
+constexpr int kSlDoneWords = 44;     // 40 sums + destination id + pad (176 B)
+constexpr int kSlWin = 10;           // row_ptr entries per register window (one per lane of a group)
+constexpr int kSlNodeCost = 2;       // a destination costs about two edges
+constexpr int kSlBoxRows = 32;       // relations per TMA box
 constexpr int kSlMaxR2 = 576;
 
 inline int sliced_w_rows(int R2) { return (R2 + kSlBoxRows - 1) / kSlBoxRows * kSlBoxRows; }
 inline size_t sliced_smem_bytes(int R2) {
-  return (size_t)sliced_w_rows(R2) * 320 + (size_t)kSlWarps * 3 * kSlRing * kSlRingWords * 4 +
+  return (size_t)sliced_w_rows(R2) * 320 + (size_t)kSlWarps * 3 * kSlDone * kSlDoneWords * 4 +
          (size_t)kSlWarps * 2 * kSlFeat * 4 + 16;
 }
 
-// Tensor map over the relation table W [R2, 400] fp32 (RGCN.py:75-77 layout) with a box of kSlBoxRows x 80 floats: one
-// TMA op moves 32 relations' columns of one slice.  Pure host computation (no allocation, nothing retained).
+// Tensor map over the relation table W [R2, 400] fp32 (RGCN.py:75-77 layout: 100 blocks of 4 floats per relation) viewed
+// as [R2][50 pairs][2 parities][4 floats], box = 32 relations x 10 pairs x 1 parity x 4 floats: one TMA op moves one parity
+// plane of 32 relations' columns of one slice.  Pure host computation (no allocation, nothing retained).
 inline int sliced_make_tmap(const float* W, int R2, CUtensorMap* tm) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -62,11 +68,11 @@ inline int sliced_make_tmap(const float* W, int R2, CUtensorMap* tm) {
     }
     fn = reinterpret_cast<EncodeFn>(p);
   }
-  const cuuint64_t dims[2] = {400, (cuuint64_t)R2};
-  const cuuint64_t strides[1] = {1600};
-  const cuuint32_t box[2] = {80, (cuuint32_t)kSlBoxRows};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(W), dims, strides, box, estr,
+  const cuuint64_t dims[4] = {4, 2, 50, (cuuint64_t)R2};
+  const cuuint64_t strides[3] = {16, 32, 1600};
+  const cuuint32_t box[4] = {4, 1, 10, (cuuint32_t)kSlBoxRows};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(W), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -75,16 +81,6 @@ inline int sliced_make_tmap(const float* W, int R2, CUtensorMap* tm) {
   }
   return RENET_OK;
 }
-
-__device__ __forceinline__ void cp_async_cg16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_ca4(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // smallest p in [0, N] with row_ptr[p] + kSlNodeCost * p >= T, for two targets at once (lanes 0-15: T0, 16-31: T1)
 __device__ __forceinline__ void warp_lower_bound2(const int32_t* __restrict__ row_ptr, int N, int64_t T0, int64_t T1,
@@ -120,14 +116,15 @@ struct SlIdx {
 template <bool RELU, bool HAS_LOOP, bool INDEXED, bool BWD>
 __global__ void __launch_bounds__(kSlThreads, 1)
 rgcn_gather_sliced_kernel(const float* __restrict__ X, const int32_t* __restrict__ x_index,
-                          const __grid_constant__ CUtensorMap w_map, const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_a,
-                          const int32_t* __restrict__ col_type, const float* __restrict__ norm, float* __restrict__ Out,
-                          int N, int R2) {
+                          const __grid_constant__ CUtensorMap w_map, const int32_t* __restrict__ row_ptr,
+                          const int32_t* __restrict__ col_a, const int32_t* __restrict__ col_type,
+                          const float* __restrict__ norm, float* __restrict__ Out, int N, int R2) {
   extern __shared__ __align__(128) uint8_t sl_smem[];
-  float* Wsm = reinterpret_cast<float*>(sl_smem);
   const int w_rows = (R2 + kSlBoxRows - 1) / kSlBoxRows * kSlBoxRows;
-  float* ring_all = Wsm + (size_t)w_rows * 80;
-  float* head_all = ring_all + kSlWarps * 3 * kSlRing * kSlRingWords;
+  float* W0 = reinterpret_cast<float*>(sl_smem);            // [w_rows][10 pairs][4]: even blocks of the slice
+  float* W1 = W0 + (size_t)w_rows * 40;                     // odd blocks
+  float* done_all = W1 + (size_t)w_rows * 40;
+  float* head_all = done_all + kSlWarps * 3 * kSlDone * kSlDoneWords;
   uint64_t* bar = reinterpret_cast<uint64_t*>(head_all + kSlWarps * 2 * kSlFeat);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slice = blockIdx.x % kSlices;
@@ -137,7 +134,7 @@ rgcn_gather_sliced_kernel(const float* __restrict__ X, const int32_t* __restrict
   const int worker = cta_in_slice * kSlWarps + warp;
   const int soff = slice * kSlFeat;
 
-  // ---- 1. this slice of the relation table -> shared memory: TMA boxes of 32 relations x 80 floats ---------------------
+  // ---- 1. this slice of the relation table -> shared memory: TMA boxes of 32 relations x 10 block pairs x one parity ----
   const uint32_t bar_a = smem_u32(bar);
   if (tid == 0) {
     mbar_init(bar_a, 1);
@@ -149,11 +146,14 @@ rgcn_gather_sliced_kernel(const float* __restrict__ X, const int32_t* __restrict
     if (lane == 0)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)w_rows * 320u) : "memory");
     __syncwarp();
-    if (lane < nbox)       // rows past R2 in the last box are filled with zeros (and never read)
-      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                       smem_u32(Wsm + lane * kSlBoxRows * 80)),
-                   "l"(reinterpret_cast<uint64_t>(&w_map)), "r"(slice * 80), "r"(lane * kSlBoxRows), "r"(bar_a)
-                   : "memory");
+    for (int i = lane; i < 2 * nbox; i += 32) {             // rows past R2 in the last box are zero-filled (and never read)
+      const int par = i & 1, bx = i >> 1;
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+              smem_u32((par ? W1 : W0) + bx * kSlBoxRows * 40)),
+          "l"(reinterpret_cast<uint64_t>(&w_map)), "r"(0), "r"(par), "r"(slice * 10), "r"(bx * kSlBoxRows), "r"(bar_a)
+          : "memory");
+    }
   }
 
   // ---- 2. this warp's destinations (overlaps the staging) -------------------------------------------------------------------
@@ -185,34 +185,18 @@ rgcn_gather_sliced_kernel(const float* __restrict__ X, const int32_t* __restrict
   }
   const bool walks = lane_on && (glen > 0 || (len == 0 && g == 0 && vb > va));
   bool continued = lane_on && glen > 0 && g > first_ne && __ldg(row_ptr + node) < ge0;
-  int node_end = walks ? __ldg(row_ptr + node + 1) : 0x7fffffff;
-  int node_beg = walks ? __ldg(row_ptr + node) : 0;          // first edge of `node`
+  // register window over row_ptr: lane j of the group holds the end of destination wbase + j (and of wbase + 10 + j)
+  int wbase = node;
+  int win = __ldg(row_ptr + min(wbase + 1 + j, N)), win2 = __ldg(row_ptr + min(wbase + 1 + kSlWin + j, N));
+  int node_end = __shfl_sync(0xffffffffu, win, gbase);
+  int node_beg = walks ? __ldg(row_ptr + node) : 0;         // first edge of `node`
+  if (!walks) node_end = 0x7fffffff;
 
-  float* ring = ring_all + (size_t)(warp * 3 + (lane_on ? g : 0)) * kSlRing * kSlRingWords;
+  float* done = done_all + (size_t)(warp * 3 + (lane_on ? g : 0)) * kSlDone * kSlDoneWords;   // this group's finished sums
   float* heads = head_all + (size_t)warp * 2 * kSlFeat;     // [2][40]: partial sums of groups 1 and 2 for a destination they continue
-  int slot = 0;                                             // ring slot of `node`
-  auto ring_prefetch = [&](int n, int s) {                  // epilogue inputs of destination n -> ring slot s
-    if (lane_on && n < N) {
-      float* dstp = ring + s * kSlRingWords;
-      if (HAS_LOOP) cp_async_cg16(dstp + 4 * j, Out + (size_t)n * 200 + soff + 4 * j);
-      if (j == 0) {
-        if (!BWD) cp_async_ca4(dstp + 40, norm + n);
-        cp_async_ca4(dstp + 41, row_ptr + n + 1);
-      }
-    }
-    cp_async_commit_group();
-  };
-#pragma unroll
-  for (int i = 0; i < kSlRing; ++i) ring_prefetch(node + i, i);
+  int cnt = 0;                                              // entries in `done`
+  float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);     // blocks 2j and 2j+1 of the slice
 
-  // lane's two blocks: 2j and 2j+1 of the slice.  Odd lane-quads read them in swapped order, which makes every
-  // quarter-warp's LDS.128 on the relation row bank-conflict free (rows are stored as the TMA delivers them)
-  const bool sw = (lane >> 2) & 1;
-  const int pa = 4 * (2 * j + (sw ? 1 : 0)), pb = 4 * (2 * j + (sw ? 0 : 1));
-  float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);
-  auto natural = [&]() {                                    // (block 2j, block 2j+1) as one float4
-    return sw ? make_float4(accB.x, accB.y, accA.x, accA.y) : make_float4(accA.x, accA.y, accB.x, accB.y);
-  };
   auto finalize = [&](int n, float4 a, float4 lp, float nv) {
     float4 o;
     if (BWD) {
@@ -223,27 +207,60 @@ rgcn_gather_sliced_kernel(const float* __restrict__ X, const int32_t* __restrict
     }
     st_f4(Out + (size_t)n * 200 + soff + 4 * j, o);
   };
-  // destination `node` is complete as far as this group is concerned: write it (or hand the partial sum over) and move on
-  auto flush = [&]() {
-    cp_async_wait_group<kSlRing - 2>();                     // ring entries of node and node+1 have landed
+  // the group's buffered destinations: epilogue inputs loaded as one batch, then norm / self-loop / activation / store
+  auto drain = [&]() {
     __syncwarp(gmask);
-    const float* sp = ring + slot * kSlRingWords;
-    const int nslot = slot + 1 == kSlRing ? 0 : slot + 1;
-    const float4 a = natural();
+#pragma unroll
+    for (int i0 = 0; i0 < kSlDone; i0 += 2) {               // two at a time: bounded register footprint
+      float4 lp[2];
+      float nv[2];
+      int nn[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        lp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        nv[i] = 1.f;
+        nn[i] = 0;
+        if (i0 + i < cnt) {
+          nn[i] = __float_as_int(done[(i0 + i) * kSlDoneWords + 40]);
+          if (HAS_LOOP) lp[i] = *reinterpret_cast<const float4*>(Out + (size_t)nn[i] * 200 + soff + 4 * j);
+          if (!BWD) nv[i] = __ldg(norm + nn[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        if (i0 + i < cnt) finalize(nn[i], *reinterpret_cast<const float4*>(done + (i0 + i) * kSlDoneWords + 4 * j), lp[i], nv[i]);
+    }
+    __syncwarp(gmask);
+    cnt = 0;
+  };
+  // destination `node` is complete as far as this group is concerned: park the sum (or hand the partial sum over), move on
+  auto flush = [&]() {
+    const float4 a = make_float4(accA.x, accA.y, accB.x, accB.y);
     if (continued) {
       *reinterpret_cast<float4*>(heads + (g - 1) * kSlFeat + 4 * j) = a;
       continued = false;
     } else {
-      const float4 lp = HAS_LOOP ? *reinterpret_cast<const float4*>(sp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      finalize(node, a, lp, BWD ? 1.f : sp[40]);
+      if (cnt == kSlDone) {                                 // rare (more than 4 destinations ended inside one block): finish it here
+        const float4 lp = HAS_LOOP ? *reinterpret_cast<const float4*>(Out + (size_t)node * 200 + soff + 4 * j)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        finalize(node, a, lp, BWD ? 1.f : __ldg(norm + node));
+      } else {
+        *reinterpret_cast<float4*>(done + cnt * kSlDoneWords + 4 * j) = a;
+        if (j == 0) done[cnt * kSlDoneWords + 40] = __int_as_float(node);
+        ++cnt;
+      }
     }
     accA = make_float2(0.f, 0.f); accB = make_float2(0.f, 0.f);
     node_beg = node_end;
-    node_end = __float_as_int(ring[nslot * kSlRingWords + 41]);
-    __syncwarp(gmask);                                      // everyone has read the old slot before it is refilled
     ++node;
-    ring_prefetch(node + kSlRing - 1, slot);
-    slot = nslot;
+    int wi = node - wbase;
+    if (wi == kSlWin) {
+      win = win2;
+      wbase += kSlWin;
+      win2 = __ldg(row_ptr + min(wbase + 1 + kSlWin + j, N));
+      wi = 0;
+    }
+    node_end = __shfl_sync(gmask, win, gbase + wi);
   };
 
   // ---- 3. wait for the relation table ---------------------------------------------------------------------------------------------
@@ -280,24 +297,24 @@ rgcn_gather_sliced_kernel(const float* __restrict__ X, const int32_t* __restrict
       const float sk = BWD ? __shfl_sync(0xffffffffu, r.sc, gbase + k) : 1.f;
       if (ee < ge1) {
         while (ee == node_end) flush();
-        const float* wr = Wsm + tk * 80;
-        const float4 wa = *reinterpret_cast<const float4*>(wr + pa), wb = *reinterpret_cast<const float4*>(wr + pb);
+        const float4 wa = *reinterpret_cast<const float4*>(W0 + tk * 40 + 4 * j);
+        const float4 wb = *reinterpret_cast<const float4*>(W1 + tk * 40 + 4 * j);
         float4 h = hb[k];
         if (BWD) { h.x *= sk; h.y *= sk; h.z *= sk; h.w *= sk; }
-        const float hax = sw ? h.z : h.x, hay = sw ? h.w : h.y, hbx = sw ? h.x : h.z, hby = sw ? h.y : h.w;
         if (!BWD) {      // out[jj] += sum_i in[i] * W[i][jj];  block = (W00 W01; W10 W11) row-major
-          accA.x = fmaf(hax, wa.x, fmaf(hay, wa.z, accA.x));
-          accA.y = fmaf(hax, wa.y, fmaf(hay, wa.w, accA.y));
-          accB.x = fmaf(hbx, wb.x, fmaf(hby, wb.z, accB.x));
-          accB.y = fmaf(hbx, wb.y, fmaf(hby, wb.w, accB.y));
+          accA.x = fmaf(h.x, wa.x, fmaf(h.y, wa.z, accA.x));
+          accA.y = fmaf(h.x, wa.y, fmaf(h.y, wa.w, accA.y));
+          accB.x = fmaf(h.z, wb.x, fmaf(h.w, wb.z, accB.x));
+          accB.y = fmaf(h.z, wb.y, fmaf(h.w, wb.w, accB.y));
         } else {         // din[i] += sum_jj W[i][jj] * g[jj]
-          accA.x = fmaf(hax, wa.x, fmaf(hay, wa.y, accA.x));
-          accA.y = fmaf(hax, wa.z, fmaf(hay, wa.w, accA.y));
-          accB.x = fmaf(hbx, wb.x, fmaf(hby, wb.y, accB.x));
-          accB.y = fmaf(hbx, wb.z, fmaf(hby, wb.w, accB.y));
+          accA.x = fmaf(h.x, wa.x, fmaf(h.y, wa.y, accA.x));
+          accA.y = fmaf(h.x, wa.z, fmaf(h.y, wa.w, accA.y));
+          accB.x = fmaf(h.z, wb.x, fmaf(h.w, wb.y, accB.x));
+          accB.y = fmaf(h.z, wb.z, fmaf(h.w, wb.w, accB.y));
         }
       }
     }
+    drain();                                                // converged: the three groups finish their destinations together
   };
   float4 hA[kSlKB], hB[kSlKB];
   SlIdx i0 = load_idx(0), i1 = load_idx(1), i2 = load_idx(2), i3;
@@ -326,13 +343,13 @@ rgcn_gather_sliced_kernel(const float* __restrict__ X, const int32_t* __restrict
   if (walks) {
     while (node < vb && node_end <= ge1) flush();
     if (glen > 0 && node < vb && node_beg < ge1) {          // this group holds edges of a destination that goes on into g+1
-      mine = natural();
+      mine = make_float4(accA.x, accA.y, accB.x, accB.y);
       if (continued) *reinterpret_cast<float4*>(heads + (g - 1) * kSlFeat + 4 * j) = mine;
       else starter = true;
     }
   }
-  cp_async_wait_group<0>();
   __syncwarp();
+  drain();
   if (starter) {                                            // sum in group order: own tail + head of g+1 (+ head of g+2)
     const float4 h1 = *reinterpret_cast<const float4*>(heads + g * kSlFeat + 4 * j);
     mine.x += h1.x; mine.y += h1.y; mine.z += h1.z; mine.w += h1.w;

@@ -239,6 +239,13 @@ class BatchedHistoryGraph:
                 torch.arange(self.N, device=self.device, dtype=torch.int32), counts)
         return self._bwd['dst']
 
+    def readout_sub(self, readout, reverse):
+        """The read-out sub-graph layer 2 runs on (ReadoutSubgraph), built once per type column."""
+        key = ('sub', bool(reverse))
+        if key not in self._bwd:
+            self._bwd[key] = ReadoutSubgraph(self, readout, reverse)
+        return self._bwd[key]
+
     def backward_structs(self, reverse, num_types):
         """(t_row_ptr, t_col_dst, t_col_type, rel_ptr, rel_src, rel_dst) for the backward kernels."""
         key = ('bwd', bool(reverse), int(num_types))
@@ -251,6 +258,89 @@ class BatchedHistoryGraph:
             t_row_ptr, t_col_dst, t_col_type, _ = build_csr(self.col_src, dst, et, self.N)
             # group by relation: key = etype, payload = (src, dst)
             rel_ptr, rel_src, rel_dst, _ = build_csr(et, self.col_src, dst, num_types)
+            self._bwd[key] = (t_row_ptr, t_col_dst, t_col_type, rel_ptr, rel_src, rel_dst)
+        return self._bwd[key]
+
+
+_CNT_PINNED = __import__('collections').deque()       # pool of pinned int32[2] read-back slots
+
+
+class ReadoutSubgraph:
+    """Layer 2's graph: only the edges whose destination is a read-out node (reference Aggregator.py:139-140 keeps
+    nothing else of layer 2's output).  Built on the device by renet_readout_subgraph, on the current stream, without
+    waiting for anything: capacities are S destinations and the parent's edge capacity; the real sizes (U distinct
+    read-out nodes, E2 edges) come back asynchronously and are only needed by backward.
+
+    Destinations are compact (row u <-> node uniq[u]); sources keep the parent's node ids (rows of H1).  Quacks like
+    BatchedHistoryGraph for the layer kernels: N (destination rows), N_src, row_ptr, col_src, col_type(), norm, E_launch."""
+
+    def __init__(self, g, readout, reverse):
+        L = _lib.lib()
+        dev = g.device
+        S = int(readout.numel())
+        self.device, self.N, self.N_src, self.reverse = dev, S, g.N, bool(reverse)
+        self.E_cap = int(g.col_src.numel())
+        i32 = torch.empty(3 * S + (S + 1) + 2 * self.E_cap + 2, dtype=torch.int32, device=dev)
+        o = 0
+        parts = {}
+        for name, n in (('uniq', S), ('readout_c', S), ('row_ptr', S + 1), ('col_src', self.E_cap), ('col_type', self.E_cap),
+                        ('norm', S), ('counts', 2)):
+            parts[name] = i32[o:o + n]
+            o += n
+        self.uniq, self.readout_c, self.row_ptr = parts['uniq'], parts['readout_c'], parts['row_ptr']
+        self.col_src, self._col_type, self.counts = parts['col_src'], parts['col_type'], parts['counts']
+        self.norm = parts['norm'].view(torch.float32)
+        nbytes = int(L.renet_readout_subgraph_workspace_bytes(g.N, S))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        P = _lib.ptr
+        rc = L.renet_readout_subgraph(P(readout), S, g.N, P(g.row_ptr), P(g.col_src), P(g.col_type(reverse)), P(g.norm),
+                                      P(self.uniq), P(self.readout_c), P(self.row_ptr), P(self.col_src), P(self._col_type),
+                                      P(self.norm), P(self.counts), P(ws), nbytes, _lib.stream())
+        _lib.check(rc, 'renet_readout_subgraph')
+        try:
+            host = _CNT_PINNED.pop()
+        except IndexError:
+            host = torch.empty(2, dtype=torch.int32).pin_memory()
+        host.copy_(self.counts, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending, self._host = ev, host
+        self._sizes = None
+        self._keep = (i32, ws)
+        self._bwd = {}
+
+    def sizes(self):
+        """(U, E2): waits for the asynchronous read-back once."""
+        if self._sizes is None:
+            self._pending.synchronize()
+            self._sizes = (int(self._host[0]), int(self._host[1]))
+            _CNT_PINNED.append(self._host)
+            self._pending = self._host = None
+        return self._sizes
+
+    @property
+    def E(self):
+        return self.sizes()[1]
+
+    @property
+    def E_launch(self):
+        return self.E_cap
+
+    def col_type(self, reverse):
+        if bool(reverse) != self.reverse:
+            raise RuntimeError('ReadoutSubgraph was built for reverse=%s' % self.reverse)
+        return self._col_type
+
+    def backward_structs(self, reverse, num_types):
+        """CSR by SOURCE (N_src keys, compact destination ids as payload) and the relation-grouped edge list."""
+        key = ('bwd', int(num_types))
+        if key not in self._bwd:
+            E2 = self.E
+            counts = (self.row_ptr[1:] - self.row_ptr[:-1]).long()
+            dst = torch.repeat_interleave(torch.arange(self.N, device=self.device, dtype=torch.int32), counts, output_size=E2)
+            src, et = self.col_src[:E2], self.col_type(reverse)[:E2]
+            t_row_ptr, t_col_dst, t_col_type, _ = build_csr(src, dst, et, self.N_src)
+            rel_ptr, rel_src, rel_dst, _ = build_csr(et, src, dst, num_types)
             self._bwd[key] = (t_row_ptr, t_col_dst, t_col_type, rel_ptr, rel_src, rel_dst)
         return self._bwd[key]
 

@@ -19,7 +19,7 @@ def _gru_params(m):
 
 class _FusedGruFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, H2, ent, rel, glob, w_ih4, w_hh4, b_ih4, b_hh4, w_ih3, w_hh3, b_ih3, b_hh3, hb, seq_s, seq_r):
+    def forward(ctx, H2, ent, rel, glob, w_ih4, w_hh4, b_ih4, b_hh4, w_ih3, w_hh3, b_ih3, b_hh3, hb, seq_s, seq_r, readout=None):
         L = _lib.lib()
         tensors = [t.contiguous() for t in (H2, ent, rel, glob, w_ih4, w_hh4, b_ih4, b_hh4, w_ih3, w_hh3, b_ih3, b_hh3)]
         _lib.require_cuda(*tensors)
@@ -32,7 +32,8 @@ class _FusedGruFn(torch.autograd.Function):
         nbytes = int(L.renet_gru_workspace_bytes(S, Q, T, h))
         ws = torch.empty(nbytes // 4 + 4, dtype=torch.float32, device=dev)
         bs = hb.batch_sizes      # host int32 numpy
-        rc = L.renet_gru_fwd(_lib.ptr(H2), _lib.ptr(hb.readout), _lib.ptr(hb.row_glob), _lib.ptr(glob),
+        readout = hb.readout if readout is None else readout
+        rc = L.renet_gru_fwd(_lib.ptr(H2), _lib.ptr(readout), _lib.ptr(hb.row_glob), _lib.ptr(glob),
                              _lib.ptr(ent), _lib.ptr(rel), _lib.ptr(seq_s), _lib.ptr(seq_r),
                              _lib.ptr(hb.graph.seq_len_dev), _lib.ptr(hb.seq_start),
                              bs.ctypes.data_as(_lib.ctypes.c_void_p), len(bs),
@@ -41,7 +42,7 @@ class _FusedGruFn(torch.autograd.Function):
                              _lib.ptr(hn4), _lib.ptr(hn3), S, Q, T, h, _lib.ptr(ws), nbytes, _lib.stream())
         _lib.check(rc, 'renet_gru_fwd')
         ctx.save_for_backward(*tensors, ws)
-        ctx.hb, ctx.seq_s, ctx.seq_r = hb, seq_s, seq_r
+        ctx.hb, ctx.seq_s, ctx.seq_r, ctx.readout = hb, seq_s, seq_r, readout
         return hn4, hn3
 
     @staticmethod
@@ -50,6 +51,7 @@ class _FusedGruFn(torch.autograd.Function):
         return fused_gru_backward(ctx, dhn4, dhn3)
 
 
-def fused_gru(H2, ent, rel, glob, hb, seq_s, seq_r, encoder, encoder_r):
+def fused_gru(H2, ent, rel, glob, hb, seq_s, seq_r, encoder, encoder_r, readout=None):
+    """``readout`` overrides hb.readout: rows of H2 the sequences read (the compact indices of the read-out sub-graph)."""
     p4, p3 = _gru_params(encoder), _gru_params(encoder_r)
-    return _FusedGruFn.apply(H2, ent, rel, glob, *p4, *p3, hb, seq_s, seq_r)
+    return _FusedGruFn.apply(H2, ent, rel, glob, *p4, *p3, hb, seq_s, seq_r, readout)

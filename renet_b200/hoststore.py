@@ -116,13 +116,17 @@ class HistoryStore:
     """Histories of a whole split (the reference's pickled train_history_{sub,ob}.txt), flattened, with every
     entity already resolved to its local row in that timestamp's graph."""
 
-    def __init__(self, hist, hist_t, subjects, graph_store, dedupe=True):
-        """hist / hist_t: the reference's per-sample lists (list[n] of list[<=L] of int arrays [k,2] / timestamps);
+    def __init__(self, hist, hist_t, subjects, graph_store, dedupe=True, reverse=None):
+        """``reverse`` (optional hint): the edge-type column these histories are used with -- False for subject histories
+        (type_s), True for object histories (type_o), model.py:65-78.  With it the batcher also builds layer 2's read-out
+        sub-graph ahead of time, on the loader stream.
+        hist / hist_t: the reference's per-sample lists (list[n] of list[<=L] of int arrays [k,2] / timestamps);
         subjects: int [n].  Vectorised: one pass over the entries to collect them, everything else in numpy.
         ``dedupe``: the reference's history lists share one array object per (entity, timestamp) among all the samples
         of that entity, so entries are keyed on (array identity, subject) and stored once; pass False for throw-away
         stores of a single batch (``view_from_lists``), where the sort that finds duplicates costs more than it saves."""
         self.gs = gs = graph_store
+        self.reverse = reverse
         n = len(hist)
         self.subjects = np.asarray(subjects, dtype=np.int64)
         lens = np.fromiter((len(h) for h in hist), dtype=np.int64, count=n)
@@ -399,6 +403,27 @@ def _upload_plan(view, buf, r, device):
                                   P(parts['row_ptr']), P(parts['col_src']), P(parts['col_type_s']), P(parts['col_type_o']),
                                   P(parts['norm']), P(parts['e_count']), P(ws), ws.numel() * 4, _lib.stream())
         _lib.check(rc, 'renet_induce_edges')
+    g = BatchedHistoryGraph.__new__(BatchedHistoryGraph)
+    g.device, g.N = torch.device(device), N
+    g.E_cap = E_cand
+    g.node_ent, g.row_ptr = d['node_ent'], parts['row_ptr']
+    g.col_src, g.col_type_s, g.col_type_o = parts['col_src'], parts['col_type_s'], parts['col_type_o']
+    g.norm = parts['norm'].view(torch.float32)
+    g.comp_sizes = None
+    g.h2d_bytes = words * 4
+    g.ndata = _Frame(norm=g.norm.view(-1, 1), id=g.node_ent.view(-1, 1))
+    g.h_index = g.h_table = None
+    g._bwd = {}
+    g.G, g.comp = r['G'], None
+    g.seq_len_dev = d['seq_len']
+    g._keep = (blob, dev)
+    with torch.cuda.stream(ls):
+        rev = getattr(view.store, 'reverse', None)
+        sub = None
+        if rev is not None:
+            # the store knows which edge-type column its histories are used with (subject histories: type_s, object
+            # histories: type_o, model.py:65-78): layer 2's read-out sub-graph is built here, on the loader stream too
+            sub = g.readout_sub(d['readout'], rev)
         ready = torch.cuda.Event()
         ready.record(ls)
         try:
@@ -411,20 +436,10 @@ def _upload_plan(view, buf, r, device):
     main.wait_event(ready)
     dev.record_stream(main)          # allocated on the loader stream, consumed on the caller's
     blob.record_stream(main)
-    g = BatchedHistoryGraph.__new__(BatchedHistoryGraph)
-    g.device, g.N = torch.device(device), N
-    g._E_pending, g.E_cap = PendingCount(e_ev, e_host, _E_PINNED.append), E_cand
-    g.node_ent, g.row_ptr = d['node_ent'], parts['row_ptr']
-    g.col_src, g.col_type_s, g.col_type_o = parts['col_src'], parts['col_type_s'], parts['col_type_o']
-    g.norm = parts['norm'].view(torch.float32)
-    g.comp_sizes = None
-    g.h2d_bytes = words * 4
-    g.ndata = _Frame(norm=g.norm.view(-1, 1), id=g.node_ent.view(-1, 1))
-    g.h_index = g.h_table = None
-    g._bwd = {}
-    g.G, g.comp = r['G'], None
-    g.seq_len_dev = d['seq_len']
-    g._keep = (blob, dev)
+    if sub is not None:
+        for t in sub._keep:
+            t.record_stream(main)
+    g._E_pending = PendingCount(e_ev, e_host, _E_PINNED.append)
     hb.graph = g
     hb.readout, hb.row_glob, hb.row_seq = d['readout'], d['row_comp'], d['row_seq']
     hb.seq_start, hb.packed_row = d['seq_start'], d['packed_row']

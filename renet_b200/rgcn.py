@@ -98,15 +98,25 @@ class _GatherFn(torch.autograd.Function):
         d_in, d_out = H.shape[1], out.shape[1]
         dout = dout.contiguous()
         t_row_ptr, t_col_dst, t_col_type, rel_ptr, rel_src, rel_dst = g.backward_structs(ctx.reverse, W.shape[0])
-        dHrows = _buf((g.N, d_in), H)
+        n_src = getattr(g, 'N_src', g.N)
+        dHrows = _buf((n_src, d_in), H)
         dW = torch.zeros_like(W)
         ws = _buf((((g.N * d_out + 3) // 4) * 4 + d_in * d_out,), H)
-        rc = L.renet_rgcn_block_bwd(_lib.ptr(H), _lib.ptr(ctx.h_index), _lib.ptr(W), None, _lib.ptr(t_row_ptr),
-                                    _lib.ptr(t_col_dst), _lib.ptr(t_col_type), _lib.ptr(rel_ptr),
-                                    _lib.ptr(rel_src), _lib.ptr(rel_dst), _lib.ptr(g.norm), _lib.ptr(out),
-                                    _lib.ptr(dout), _lib.ptr(dHrows), _lib.ptr(dW), None, _lib.ptr(ws), g.N, g.E,
-                                    d_in, d_out, ctx.nb, W.shape[0], int(ctx.relu), _lib.stream())
-        _lib.check(rc, 'renet_rgcn_block_bwd')
+        if n_src != g.N or hasattr(g, 'N_src'):
+            # read-out sub-graph (layer 2): compact destinations, full-graph sources
+            rc = L.renet_rgcn_bipartite_bwd(_lib.ptr(H), _lib.ptr(W), _lib.ptr(t_row_ptr), _lib.ptr(t_col_dst),
+                                            _lib.ptr(t_col_type), _lib.ptr(rel_ptr), _lib.ptr(rel_src), _lib.ptr(rel_dst),
+                                            _lib.ptr(g.norm), _lib.ptr(out), _lib.ptr(dout), _lib.ptr(dHrows), _lib.ptr(dW),
+                                            _lib.ptr(ws), n_src, g.N, g.E, d_in, d_out, ctx.nb, W.shape[0], int(ctx.relu),
+                                            _lib.stream())
+            _lib.check(rc, 'renet_rgcn_bipartite_bwd')
+        else:
+            rc = L.renet_rgcn_block_bwd(_lib.ptr(H), _lib.ptr(ctx.h_index), _lib.ptr(W), None, _lib.ptr(t_row_ptr),
+                                        _lib.ptr(t_col_dst), _lib.ptr(t_col_type), _lib.ptr(rel_ptr),
+                                        _lib.ptr(rel_src), _lib.ptr(rel_dst), _lib.ptr(g.norm), _lib.ptr(out),
+                                        _lib.ptr(dout), _lib.ptr(dHrows), _lib.ptr(dW), None, _lib.ptr(ws), g.N, g.E,
+                                        d_in, d_out, ctx.nb, W.shape[0], int(ctx.relu), _lib.stream())
+            _lib.check(rc, 'renet_rgcn_block_bwd')
         dloop = ws[:g.N * d_out].view(g.N, d_out) if ctx.has_loop else None     # P = dout * act'(out)
         return _rows_to_table_grad(dHrows, ctx.h_index, H), dW, dloop, None, None, None, None, None, None
 
@@ -166,12 +176,15 @@ class RGCNBlockLayer(RGCNLayer):
         g.h_table = g.h_index = None
         return g
 
-    def apply_layer(self, g, H, h_index, reverse):
+    def apply_layer(self, g, H, h_index, reverse, loop_index=None):
+        """One layer over graph ``g``.  ``h_index``: rows of H are addressed through it (fused embedding lookup);
+        ``loop_index`` (read-out sub-graph): destination u's own feature row is H[loop_index[u]] while edge sources
+        address H directly."""
         if isinstance(self.bias, nn.Parameter):                 # RGCN.py:43-44 (never used by RE-Net)
             raise RuntimeError('RGCNBlockLayer(bias=True) is not supported by the fused kernel')
         loop = None
         if self.self_loop:
-            loop = _SelfLoopFn.apply(H, self.loop_weight, h_index, g.N)
+            loop = _SelfLoopFn.apply(H, self.loop_weight, h_index if loop_index is None else loop_index, g.N)
             if self.dropout is not None:
                 loop = self.dropout(loop)                       # RGCN.py:36-37
         fuse_relu = self._relu_fused()

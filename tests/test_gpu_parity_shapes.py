@@ -195,3 +195,44 @@ def test_aggregator_forward_predict_batch_predict_vs_reference(tag, fname):
             assert rel_err(q4.data[rows].cpu().numpy(), gold[key + 'rank_x4']) < TOL
             assert rel_err(q3.data[rows].cpu().numpy(), gold[key + 'rank_x3']) < TOL
             assert rel_err(q4.data.double().sum(0).cpu().numpy(), gold[key + 'rank_x4_sum']) < TOL
+
+
+def test_readout_subgraph_layer2_equals_full_layer2(bench_tkg):
+    """Layer 2 on the read-out sub-graph (renet_readout_subgraph; Aggregator.py:140 keeps only the read-out rows) gives
+    BIT-identical values on every consumed row to layer 2 on the whole batched graph, the structure matches a numpy
+    restatement, and the whole direction (RENet.encode, autograd and no-grad paths) equals the CPU oracle."""
+    import gpu_helpers as G
+    from renet_b200 import utils
+    tkg = bench_tkg
+    q, sh, oh = tkg.batch(1, 1024, tail_only=False)
+    ent, W1, L1, W2, L2 = _weights(tkg.num_e, 2 * tkg.num_r, seed=3)
+    dW = [x.to(DEV) for x in (ent, W1, L1, W2, L2)]
+    for hist, col, reverse in ((sh, 0, False), (oh, 2, True)):
+        hb = utils.assemble_history_batch(hist[0], hist[1], q[:, col], tkg.graph_dict, torch.device(DEV))
+        g = hb.graph
+        sub = g.readout_sub(hb.readout, reverse)
+        U, E2 = sub.sizes()
+        ro = hb.readout.cpu().numpy()
+        uniq = np.unique(ro)
+        rp = g.row_ptr.cpu().numpy()
+        assert U == len(uniq) and np.array_equal(sub.uniq[:U].cpu().numpy(), uniq)
+        assert np.array_equal(sub.readout_c.cpu().numpy(), np.searchsorted(uniq, ro))
+        deg = (rp[1:] - rp[:-1])[uniq]
+        assert E2 == deg.sum() and np.array_equal(sub.row_ptr[:U + 1].cpu().numpy(), np.concatenate(([0], np.cumsum(deg))))
+        assert (sub.row_ptr[U:].cpu().numpy() == E2).all()
+        idx = np.concatenate([np.arange(rp[v], rp[v + 1]) for v in uniq])
+        assert np.array_equal(sub.col_src[:E2].cpu().numpy(), g.col_src.cpu().numpy()[idx])
+        assert np.array_equal(sub.col_type(reverse)[:E2].cpu().numpy(), g.col_type(reverse).cpu().numpy()[idx])
+        assert torch.equal(sub.norm[:U], g.norm[torch.from_numpy(uniq).to(DEV)])
+        ct = g.col_type(reverse)
+        h1 = G.layer_fwd(dW[0], g.node_ent, dW[1], dW[2], g.row_ptr, g.col_src, ct, g.norm, g.N, g.E, 200, 200, 100, True)
+        full = G.layer_fwd(h1, None, dW[3], dW[4], g.row_ptr, g.col_src, ct, g.norm, g.N, g.E, 200, 200, 100, False)
+        from renet_b200 import _lib
+        L, P = _lib.lib(), _lib.ptr
+        h2c = torch.empty(sub.N, 200, device=DEV)
+        _lib.check(L.renet_selfloop_gemm(P(h1), P(sub.uniq), P(dW[4]), P(h2c), sub.N, 200, 200, _lib.stream()), 'gemm')
+        _lib.check(L.renet_rgcn_gather(P(h1), None, P(dW[3]), P(sub.row_ptr), P(sub.col_src), P(sub.col_type(reverse)), P(sub.norm),
+                                       P(h2c), sub.N, sub.E_cap, 200, 200, 100, 2 * tkg.num_r, 0, 1, _lib.stream()), 'gather')
+        got = h2c[sub.readout_c.long()]
+        want = full[hb.readout.long()]
+        assert rel_err(got.cpu().numpy(), want.cpu().numpy()) < 1e-6       # same kernels, same edge order per destination

@@ -211,6 +211,7 @@ def test_sliced_kernel_edge_cases_fwd_bwd_vs_oracle(G, N, E, heavy, empty_frac):
     with torch.no_grad():
         pre = restate.rgcn_block_layer(H, W, Wl, t(src), t(dst), t(et), t(norm), False, 100)
     Gout = torch.randn(ref.shape) * (pre.abs() > 1e-4)
+    (ref * Gout).sum().backward()
     rp, cs, ct = G.csr_from_coo(src, dst, et, N)
     Hd, Wd, Wld, nd = H.to(G.DEV), W.to(G.DEV), Wl.to(G.DEV), G.d(norm)
     out = G.layer_fwd(Hd, None, Wd, Wld, rp, cs, ct, nd, N, E, 200, 200, 100, True)
