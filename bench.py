@@ -31,8 +31,20 @@ import time
 # for optimal performance in your application as needed").  Measured on a 2-GPU box: with 1 the end-to-end loop ran at
 # 6.75 ms/step per rank, with 8 at 1.52 ms/step; the kernels' own numbers do not depend on it.  Must happen before numpy /
 # torch load their OpenMP runtime.
+def _rank_cpu_budget():
+    """CPUs this rank may reasonably use: (cgroup quota or visible CPUs) / ranks on this host."""
+    n = os.cpu_count() or 1
+    try:
+        _q, _per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if _q != 'max':
+            n = min(n, max(1, int(float(_q) / float(_per))))
+    except Exception:
+        pass
+    return max(1, n // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1')))))
+
+
 if os.environ.get('OMP_NUM_THREADS') == '1' and 'LOCAL_RANK' in os.environ:
-    os.environ['OMP_NUM_THREADS'] = '8'
+    os.environ['OMP_NUM_THREADS'] = str(max(1, min(8, _rank_cpu_budget() // 3)))
 
 # Under a cgroup CPU quota far below the visible core count (16-24 CPUs of 128 on the GPU boxes) an OpenMP pool sized by
 # the core count only burns the quota in spin-waits: size it by the quota.
@@ -321,6 +333,10 @@ def run_ours(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    # before any worker thread exists: keep this rank (loader threads, OpenMP pool, consumer) on its GPU's NUMA node and
+    # on its own share of the cores
+    from renet_b200 import affinity
+    pin = affinity.pin_rank(local, int(os.environ.get('LOCAL_WORLD_SIZE', world))) if world > 1 else {'pinned': False, 'why': '1 rank'}
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device -- the hot path has no CPU fallback')
     torch.cuda.set_device(local)
@@ -558,7 +574,7 @@ def run_ours(args):
         quota = _cpu_quota()
         E2E_DEPTH = 4
         hoststore.reserve_pinned(4 * (E2E_DEPTH + 3))     # every staging buffer the loader can need, pinned up front
-        E2E_WORKERS = 8 if not quota else max(2, min(8, int(quota / max(world, 1)) - 2))
+        E2E_WORKERS = max(2, min(8, _rank_cpu_budget() - int(os.environ.get('OMP_NUM_THREADS', '1')) - 1))
         k_e2e = max(4, args.steps)
         # one full rotation over the pool of batches: the loader, the pinned pool and the caching allocator (whose block
         # sizes depend on the batch) have reached steady state before the clock starts
@@ -570,7 +586,8 @@ def run_ours(args):
             b = tt.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
             dt, msgs = a[0].item(), b[1].item()
         e2e = {'value': msgs / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d / k_e2e), 'd2h_bytes_per_step': int(d2h / k_e2e),
-               'ms_per_step': dt / k_e2e * 1e3, 'steps': k_e2e, 'warmup': w_e2e,
+               'ms_per_step': dt / k_e2e * 1e3, 'steps': k_e2e, 'warmup': w_e2e, 'cpu_pinning': pin,
+               'host_threads': {'loader': E2E_WORKERS, 'omp': int(os.environ.get('OMP_NUM_THREADS', '0') or 0), 'rank_cpu_budget': _rank_cpu_budget()},
                'batcher': 'device (renet_host_plan_batch + renet_induce_edges)' if hoststore.DEVICE_EDGES else
                           'host (renet_host_assemble_batch)',
                'what': 'RENet.encode x2 directions from HOST inputs (flat history store + triplets; the per-timestamp graph '
