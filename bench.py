@@ -64,7 +64,15 @@ sys.path.insert(0, ROOT)
 H_DIM, NUM_BASES, BATCH = 200, 100, 1024
 METRIC = 'rgcn_aggregate_edge_messages_per_sec'
 UNIT = 'edge-msg/s'
-WORKLOAD = 'ICEWS18-shaped synthetic TKG (23033 ent, 256 rel, 240 timestamps), n_hidden=200 num_bases=100 batch=1024'
+WORKLOADS = {
+    # name: (synthetic preset, timestamps, description) -- BASELINE.json configs[1] / configs[2] / configs[4]
+    'icews18': ('icews18', 240, 'ICEWS18-shaped synthetic TKG (23033 ent, 256 rel, 240 timestamps), n_hidden=200 num_bases=100 batch=1024'),
+    'gdelt': ('gdelt', 2138, 'GDELT-shaped synthetic TKG (7691 ent, 240 rel, 2138 timestamps; ~2100 components per batch), n_hidden=200 '
+                             'num_bases=100 seq-len=10 batch=1024'),
+    'synth1m': (None, 250, 'synthetic TKG shard: 1M entities / 500 relations / 250 timesteps per GPU, avg in-degree 32 (N=1M nodes, '
+                           'E=32M directed edges per GPU), n_hidden=200 num_bases=100; aggregate + GRU only'),
+}
+WORKLOAD = WORKLOADS['icews18'][2]
 
 
 def parse():
@@ -73,7 +81,9 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--timestamps', type=int, default=240)
+    ap.add_argument('--workload', default='icews18', choices=sorted(WORKLOADS))
+    ap.add_argument('--timestamps', type=int, default=None)
+    ap.add_argument('--synth-nodes', type=int, default=1_000_000, help='synth1m: nodes per GPU (edges = 32 x nodes)')
     ap.add_argument('--pool', type=int, default=8, help='distinct pre-built batches the timed steps rotate over')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -238,7 +248,7 @@ def run_reference(args):
         return
     import torch
     from renet_b200 import synthetic
-    tkg = synthetic.SyntheticTKG('icews18', seed=999, num_timestamps=args.timestamps, h_dim=H_DIM)
+    tkg = synthetic.SyntheticTKG(WORKLOADS[args.workload][0] or 'icews18', seed=999, num_timestamps=args.timestamps, h_dim=H_DIM)
     steps = max(1, min(args.steps, 5))
     res = cpu_reference_sample(tkg, torch, steps, max(1, min(args.warmup, 1)))
     line = {'impl': 'reference', 'metric': METRIC, 'value': res['value'], 'unit': UNIT, 'n_gpus': args.gpus,
@@ -346,7 +356,7 @@ def run_ours(args):
     L = _lib.lib()
 
     # ---- workload: every rank owns its own shard of the stream (weak scaling, no data-path collective)
-    tkg = synthetic.SyntheticTKG('icews18', seed=999 + rank, num_timestamps=args.timestamps, h_dim=H_DIM)
+    tkg = synthetic.SyntheticTKG(WORKLOADS[args.workload][0], seed=999 + rank, num_timestamps=args.timestamps, h_dim=H_DIM)
     torch.manual_seed(999)
     model = RENet(tkg.num_e, H_DIM, tkg.num_r, dropout=0).to(dev).eval()
     model.global_emb = {t: v.to(dev) for t, v in tkg.global_emb.items()}
@@ -629,7 +639,13 @@ def run_ours(args):
 
 if __name__ == '__main__':
     a = parse()
-    if a.impl == 'reference':
+    if a.timestamps is None:
+        a.timestamps = WORKLOADS[a.workload][1]
+    WORKLOAD = WORKLOADS[a.workload][2]
+    if a.workload == 'synth1m' and a.impl != 'reference':
+        from bench_synth import run_synth1m
+        run_synth1m(a, WORKLOAD, METRIC, UNIT, ClockSampler, measured_peak_gbs)
+    elif a.impl == 'reference':
         run_reference(a)
     else:
         run_ours(a)

@@ -218,6 +218,41 @@ int renet_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_gl
                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Read-out + concat + GRU with INPUT DROPOUT (training with the reference's default --dropout 0.5): Aggregator.py:157-158
+ * drops elements of the two padded input tensors independently (two nn.Dropout calls on [Q,10,4h] and [Q,10,3h]) before
+ * pack_padded_sequence.  With a mask per (row, column) the column-wise split of the input projection no longer applies,
+ * so the masked inputs X4d [S,4h] / X3d [S,3h] are materialised once (in the workspace, kept for backward) and projected
+ * by two tensor-core GEMMs; the recurrence is the same kernel as renet_gru_fwd.  Masks: Philox4x32-10 keyed by `seed`,
+ * counter = element index (X4 element (row i, col c): i*4h + c; X3 element: S*4h + i*3h + c, rows sequence-major); kept
+ * elements are scaled by 1/(1-p).  Nothing of the mask is stored: renet_gru_bwd_dropout regenerates it from (seed, p), and
+ * renet_dropout_mask writes the same scale factors (0 or 1/(1-p)) for elements [offset, offset+n) so that tests can rebuild
+ * the exact masked inputs.  The reference's own mask stream (torch's generator) cannot be reproduced; parity is exact GIVEN
+ * the mask and statistical otherwise.  row_seq [S]: sequence of every row.  Needs the tensor-core GEMM engine.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t renet_gru_dropout_workspace_bytes(int64_t S, int64_t Q, int64_t T, int32_t h);
+int renet_gru_fwd_dropout(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
+                          const float* ent, const float* rel, const int32_t* row_seq, const int32_t* seq_s,
+                          const int32_t* seq_r, const int32_t* seq_len, const int32_t* seq_start,
+                          const int32_t* host_batch_sizes, int32_t max_len,
+                          const float* w_ih4, const float* w_hh4, const float* b_ih4, const float* b_hh4,
+                          const float* w_ih3, const float* w_hh3, const float* b_ih3, const float* b_hh3,
+                          float* hn4, float* hn3, int64_t S, int64_t Q, int64_t T, int32_t h, float p, uint64_t seed,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+int64_t renet_gru_bwd_dropout_workspace_bytes(int64_t S, int64_t Q, int64_t T, int32_t h);
+int renet_gru_bwd_dropout(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
+                          const float* ent, const float* rel, const int32_t* row_seq, const int32_t* seq_s,
+                          const int32_t* seq_r, const int32_t* seq_len, const int32_t* seq_start,
+                          const int32_t* host_batch_sizes, int32_t max_len,
+                          const float* w_ih4, const float* w_hh4, const float* w_ih3, const float* w_hh3,
+                          const float* dhn4, const float* dhn3,
+                          float* dH2, float* d_ent, float* d_rel, float* d_glob,
+                          float* dw_ih4, float* dw_hh4, float* db_ih4, float* db_hh4,
+                          float* dw_ih3, float* dw_hh3, float* db_ih3, float* db_hh3,
+                          int64_t N, int64_t S, int64_t Q, int64_t T, int32_t h, float p, uint64_t seed,
+                          const void* fwd_workspace, void* bwd_workspace, int64_t bwd_workspace_bytes, void* stream);
+int renet_dropout_mask(uint64_t seed, uint64_t offset, int64_t n, float p, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * HOST-side batching of history graphs (no CUDA; every pointer here is a HOST pointer).  Replaces
  * utils.get_sorted_s_r_embed_rgcn / get_s_r_embed_rgcn minus the embedding lookups (utils.py:209-283):
  * get_neighs_by_t :149-156, get_g_list_id + make_subgraph :158-170,115-131, get_node_ids_to_g_id

@@ -157,7 +157,9 @@ class RGCNAggregator(nn.Module):
             H2, readout = self.aggregate(hb, ent_embeds, reverse)
             glob = global_rows_of_batch(global_emb, hb, self.h_dim, dev)
             _, _, seq_s, seq_r = self._sorted_ids(hb, s, r, dev)
-            s_h, s_q = fused_gru(H2, ent_embeds, rel_embeds, glob, hb, seq_s, seq_r, encoder, encoder_r, readout=readout)
+            p_drop = self.dropout.p if self.training else 0.0          # Aggregator.py:157-158
+            s_h, s_q = fused_gru(H2, ent_embeds, rel_embeds, glob, hb, seq_s, seq_r, encoder, encoder_r, readout=readout,
+                                 p_drop=p_drop)
             return s_h, s_q, hb
 
     def _encode_inference(self, hb, s, r, ent_embeds, rel_embeds, global_emb, reverse, encoder, encoder_r, triplets=None):

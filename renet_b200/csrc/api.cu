@@ -34,14 +34,16 @@ int launch_selfloop_bwd(const float* H, const int32_t* h_index, const float* Wlo
                         float* dWloop, float* WloopT_ws, int64_t N, int d_in, int d_out, cudaStream_t stream);
 int launch_scatter_add_rows(const float* src, const int32_t* index, float* dst, int64_t n_rows, int d,
                             cudaStream_t stream);
-int64_t gru_workspace_floats(int64_t S, int64_t Q, int64_t T, int h);
+int64_t gru_workspace_floats(int64_t S, int64_t Q, int64_t T, int h, bool dropout = false);
 int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
                    const float* ent, const float* rel, const int32_t* seq_s, const int32_t* seq_r,
                    const int32_t* seq_len, const int32_t* seq_start, const int32_t* host_batch_sizes,
                    int max_len, const float* w_ih4, const float* w_hh4, const float* b_ih4, const float* b_hh4,
                    const float* w_ih3, const float* w_hh3, const float* b_ih3, const float* b_hh3, float* hn4,
-                   float* hn3, int64_t S, int64_t Q, int64_t T, int h, float* ws_base, cudaStream_t stream);
-int64_t gru_bwd_workspace_floats(int64_t S, int64_t Q, int64_t T, int h);
+                   float* hn3, int64_t S, int64_t Q, int64_t T, int h, float* ws_base, cudaStream_t stream, float p_drop = 0.f,
+                   uint64_t seed = 0, const int32_t* row_seq = nullptr);
+int64_t gru_bwd_workspace_floats(int64_t S, int64_t Q, int64_t T, int h, bool dropout = false);
+int launch_dropout_mask(uint64_t seed, uint64_t offset, int64_t n, float p, float* out, cudaStream_t stream);
 int launch_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
                    const float* ent, const float* rel, const int32_t* seq_s, const int32_t* seq_r,
                    const int32_t* seq_len, const int32_t* seq_start, const int32_t* host_batch_sizes, int max_len,
@@ -49,7 +51,8 @@ int launch_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_g
                    const float* dhn4, const float* dhn3, float* dH2, float* d_ent, float* d_rel, float* d_glob,
                    float* dw_ih4, float* dw_hh4, float* db_ih4, float* db_hh4, float* dw_ih3, float* dw_hh3,
                    float* db_ih3, float* db_hh3, int64_t N, int64_t S, int64_t Q, int64_t T, int h,
-                   const float* fwd_ws, float* bwd_ws, cudaStream_t stream);
+                   const float* fwd_ws, float* bwd_ws, cudaStream_t stream, float p_drop = 0.f, uint64_t seed = 0,
+                   const int32_t* row_seq = nullptr);
 int launch_pack_inputs(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
                        const float* ent, const float* rel, const int32_t* row_seq, const int32_t* seq_s,
                        const int32_t* seq_r, const int32_t* packed_row, float* X4, float* X3, int64_t S, int h,
@@ -318,6 +321,64 @@ int renet_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_gl
                         max_len, w_ih4, w_hh4, w_ih3, w_hh3, dhn4, dhn3, dH2, d_ent, d_rel, d_glob, dw_ih4, dw_hh4,
                         db_ih4, db_hh4, dw_ih3, dw_hh3, db_ih3, db_hh3, N, S, Q, T, h, (const float*)fwd_workspace,
                         (float*)bwd_workspace, (cudaStream_t)stream);
+}
+
+int64_t renet_gru_dropout_workspace_bytes(int64_t S, int64_t Q, int64_t T, int32_t h) {
+  return gru_workspace_floats(S, Q, T, h, true) * (int64_t)sizeof(float);
+}
+int64_t renet_gru_bwd_dropout_workspace_bytes(int64_t S, int64_t Q, int64_t T, int32_t h) {
+  return gru_bwd_workspace_floats(S, Q, T, h, true) * (int64_t)sizeof(float);
+}
+
+int renet_gru_fwd_dropout(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
+                          const float* ent, const float* rel, const int32_t* row_seq, const int32_t* seq_s,
+                          const int32_t* seq_r, const int32_t* seq_len, const int32_t* seq_start,
+                          const int32_t* host_batch_sizes, int32_t max_len, const float* w_ih4, const float* w_hh4,
+                          const float* b_ih4, const float* b_hh4, const float* w_ih3, const float* w_hh3, const float* b_ih3,
+                          const float* b_hh3, float* hn4, float* hn3, int64_t S, int64_t Q, int64_t T, int32_t h, float p,
+                          uint64_t seed, void* workspace, int64_t workspace_bytes, void* stream) {
+  RENET_CHECK_ARG(S >= 0 && Q >= 0 && T >= 0 && h > 0 && max_len >= 0, "renet_gru_fwd_dropout: bad shape");
+  RENET_CHECK_ARG(p > 0.f && p < 1.f, "renet_gru_fwd_dropout: p must be in (0, 1); use renet_gru_fwd for p = 0");
+  if (S == 0 || Q == 0) return RENET_OK;
+  RENET_CHECK_ARG(H2 && readout && row_glob && glob && ent && rel && row_seq && seq_s && seq_r && seq_len && seq_start &&
+                      host_batch_sizes && w_ih4 && w_hh4 && b_ih4 && b_hh4 && w_ih3 && w_hh3 && b_ih3 && b_hh3 && hn4 &&
+                      hn3 && workspace, "renet_gru_fwd_dropout: null pointer");
+  RENET_CHECK_ARG(workspace_bytes >= renet_gru_dropout_workspace_bytes(S, Q, T, h), "renet_gru_fwd_dropout: workspace too small");
+  RENET_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 127) == 0, "renet_gru_fwd_dropout: workspace must be 128-byte aligned");
+  return launch_gru_fwd(H2, readout, row_glob, glob, ent, rel, seq_s, seq_r, seq_len, seq_start, host_batch_sizes, max_len,
+                        w_ih4, w_hh4, b_ih4, b_hh4, w_ih3, w_hh3, b_ih3, b_hh3, hn4, hn3, S, Q, T, h, (float*)workspace,
+                        (cudaStream_t)stream, p, seed, row_seq);
+}
+
+int renet_gru_bwd_dropout(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
+                          const float* ent, const float* rel, const int32_t* row_seq, const int32_t* seq_s,
+                          const int32_t* seq_r, const int32_t* seq_len, const int32_t* seq_start,
+                          const int32_t* host_batch_sizes, int32_t max_len, const float* w_ih4, const float* w_hh4,
+                          const float* w_ih3, const float* w_hh3, const float* dhn4, const float* dhn3, float* dH2,
+                          float* d_ent, float* d_rel, float* d_glob, float* dw_ih4, float* dw_hh4, float* db_ih4,
+                          float* db_hh4, float* dw_ih3, float* dw_hh3, float* db_ih3, float* db_hh3, int64_t N, int64_t S,
+                          int64_t Q, int64_t T, int32_t h, float p, uint64_t seed, const void* fwd_workspace,
+                          void* bwd_workspace, int64_t bwd_workspace_bytes, void* stream) {
+  RENET_CHECK_ARG(N >= 0 && S >= 0 && Q >= 0 && T >= 0 && h > 0 && max_len >= 0, "renet_gru_bwd_dropout: bad shape");
+  RENET_CHECK_ARG(p > 0.f && p < 1.f, "renet_gru_bwd_dropout: p must be in (0, 1)");
+  if (S == 0 || Q == 0) return RENET_OK;
+  RENET_CHECK_ARG(H2 && readout && row_glob && glob && ent && rel && row_seq && seq_s && seq_r && seq_len && seq_start &&
+                      host_batch_sizes && w_ih4 && w_hh4 && w_ih3 && w_hh3 && dhn4 && dhn3 && dH2 && d_ent && d_rel && dw_ih4 &&
+                      dw_hh4 && db_ih4 && db_hh4 && dw_ih3 && dw_hh3 && db_ih3 && db_hh3 && fwd_workspace && bwd_workspace,
+                  "renet_gru_bwd_dropout: null pointer");
+  RENET_CHECK_ARG(bwd_workspace_bytes >= renet_gru_bwd_dropout_workspace_bytes(S, Q, T, h),
+                  "renet_gru_bwd_dropout: workspace too small");
+  return launch_gru_bwd(H2, readout, row_glob, glob, ent, rel, seq_s, seq_r, seq_len, seq_start, host_batch_sizes, max_len, w_ih4,
+                        w_hh4, w_ih3, w_hh3, dhn4, dhn3, dH2, d_ent, d_rel, d_glob, dw_ih4, dw_hh4, db_ih4, db_hh4, dw_ih3,
+                        dw_hh3, db_ih3, db_hh3, N, S, Q, T, h, (const float*)fwd_workspace, (float*)bwd_workspace,
+                        (cudaStream_t)stream, p, seed, row_seq);
+}
+
+int renet_dropout_mask(uint64_t seed, uint64_t offset, int64_t n, float p, float* out, void* stream) {
+  RENET_CHECK_ARG(n >= 0 && p >= 0.f && p < 1.f, "renet_dropout_mask: bad arguments");
+  if (n == 0) return RENET_OK;
+  RENET_CHECK_ARG(out != nullptr, "renet_dropout_mask: null pointer");
+  return launch_dropout_mask(seed, offset, n, p, out, (cudaStream_t)stream);
 }
 
 int renet_encode_fwd(const float* ent, const int32_t* node_ent, const int32_t* row_ptr, const int32_t* col_src,

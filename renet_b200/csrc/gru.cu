@@ -101,9 +101,98 @@ __global__ void pack_inputs_kernel(const float* __restrict__ H2, const int32_t* 
   }
 }
 
+
+// ---- input dropout (Aggregator.py:157-158) -----------------------------------------------------------------------------------
+// The reference drops elements of the padded GRU inputs [Q,10,4h] and [Q,10,3h] independently (two nn.Dropout calls).
+// With dropout the column-wise split of W_ih.x no longer applies (ent[s], rel[r], glob[t] get a different mask at every
+// step), so the masked inputs are materialised once (sequence-major rows, S x 4h and S x 3h) and projected by two
+// tensor-core GEMMs; the recurrence kernel is unchanged.  Masks come from Philox4x32-10 keyed by (seed, element index):
+// nothing is stored, the backward pass regenerates them.
+__device__ __forceinline__ uint4 philox4x32_10(uint64_t ctr, uint64_t key) {
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0u, c3 = 0u;
+  uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// keep-scale of element idx: 0 (dropped, probability p) or 1/(1-p)
+__device__ __forceinline__ float dropout_scale(uint64_t idx, uint64_t seed, float p, float inv_keep) {
+  const uint4 r = philox4x32_10(idx >> 2, seed);
+  const uint32_t w = (idx & 3) == 0 ? r.x : ((idx & 3) == 1 ? r.y : ((idx & 3) == 2 ? r.z : r.w));
+  return (w * 2.3283064365386963e-10f) >= p ? inv_keep : 0.f;
+}
+
+__global__ void dropout_mask_kernel(uint64_t seed, uint64_t offset, int64_t n, float p, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = dropout_scale(offset + (uint64_t)i, seed, p, 1.f / (1.f - p));
+}
+
+// masked inputs, sequence-major: row i = (sequence row_seq[i], its step i - seq_start[q])
+__global__ void pack_inputs_dropout_kernel(const float* __restrict__ H2, const int32_t* __restrict__ readout,
+                                           const int32_t* __restrict__ row_glob, const float* __restrict__ glob,
+                                           const float* __restrict__ ent, const float* __restrict__ rel,
+                                           const int32_t* __restrict__ row_seq, const int32_t* __restrict__ seq_s,
+                                           const int32_t* __restrict__ seq_r, float* __restrict__ X4,
+                                           float* __restrict__ X3, int64_t S, int h, float p, uint64_t seed) {
+  const int64_t row = blockIdx.x;
+  if (row >= S) return;
+  const int q = row_seq[row];
+  const float* src[4] = {H2 + (int64_t)readout[row] * h, ent + (int64_t)seq_s[q] * h, rel + (int64_t)seq_r[q] * h,
+                         glob + (int64_t)row_glob[row] * h};
+  const float inv = 1.f / (1.f - p);
+  const uint64_t base4 = (uint64_t)row * 4 * h, base3 = (uint64_t)S * 4 * h + (uint64_t)row * 3 * h;
+  for (int c = threadIdx.x; c < 4 * h; c += blockDim.x) {
+    const int part = c / h, k = c - part * h;
+    const float v = src[part][k];
+    X4[row * 4 * h + c] = v * dropout_scale(base4 + c, seed, p, inv);
+    if (part != 2) {                                   // X3 = [row | ent | glob]
+      const int c3 = (part == 3 ? 2 * h : part * h) + k;
+      X3[row * 3 * h + c3] = v * dropout_scale(base3 + c3, seed, p, inv);
+    }
+  }
+}
+
+// backward of the above: masked input gradients scattered to H2 rows / ent / rel / glob
+__global__ void unpack_inputs_dropout_kernel(const float* __restrict__ dX4, const float* __restrict__ dX3,
+                                             const int32_t* __restrict__ readout, const int32_t* __restrict__ row_glob,
+                                             const int32_t* __restrict__ row_seq, const int32_t* __restrict__ seq_s,
+                                             const int32_t* __restrict__ seq_r, float* __restrict__ dH2,
+                                             float* __restrict__ d_ent, float* __restrict__ d_rel, float* __restrict__ d_glob,
+                                             int64_t S, int h, float p, uint64_t seed) {
+  const int64_t row = blockIdx.x;
+  if (row >= S) return;
+  const int q = row_seq[row];
+  float* dst[4] = {dH2 + (int64_t)readout[row] * h, d_ent + (int64_t)seq_s[q] * h, d_rel + (int64_t)seq_r[q] * h,
+                   d_glob != nullptr ? d_glob + (int64_t)row_glob[row] * h : nullptr};
+  const float inv = 1.f / (1.f - p);
+  const uint64_t base4 = (uint64_t)row * 4 * h, base3 = (uint64_t)S * 4 * h + (uint64_t)row * 3 * h;
+  for (int c = threadIdx.x; c < 4 * h; c += blockDim.x) {
+    const int part = c / h, k = c - part * h;
+    float gsum = dX4[row * 4 * h + c] * dropout_scale(base4 + c, seed, p, inv);
+    if (part != 2) {
+      const int c3 = (part == 3 ? 2 * h : part * h) + k;
+      gsum += dX3[row * 3 * h + c3] * dropout_scale(base3 + c3, seed, p, inv);
+    }
+    if (dst[part] != nullptr && gsum != 0.f) atomicAdd(dst[part] + k, gsum);
+  }
+}
+
+// PQ[q, :] = b_ih (both encoders) for every sequence
+__global__ void fill_rows_kernel(const float* __restrict__ v, float* __restrict__ out, int64_t rows, int cols) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * cols) out[i] = v[i % cols];
+}
+
 struct GruWs {
   float *Brow, *Bent, *Brel, *Bglob, *Whh, *bih, *bhh, *GI, *PQ, *PT, *GH, *Hs;
   float *P_row, *P_ent, *P_rel, *P_glob, *P_hh;   // tensor-core engine: weights packed for umma_gemm_prepacked
+  float *Xd4, *Xd3, *P_x4, *P_x3;                   // input-dropout path: masked inputs [S,4h] / [S,3h], packed W_ih
   float* sync;                                      // grid-barrier counter of the persistent recurrence kernel
   int64_t p_hh_bytes;
   int64_t total_floats;
@@ -111,7 +200,7 @@ struct GruWs {
 
 inline int64_t align4(int64_t x) { return (x + 3) & ~int64_t(3); }
 
-GruWs carve(float* base, int64_t S, int64_t Q, int64_t T, int h, int max_len) {
+GruWs carve(float* base, int64_t S, int64_t Q, int64_t T, int h, int max_len, bool dropout = false) {
   GruWs w;
   int64_t off = 0;
   auto take = [&](int64_t n) { float* p = base ? base + off : nullptr; off += align4(n); return p; };
@@ -135,6 +224,14 @@ GruWs carve(float* base, int64_t S, int64_t Q, int64_t T, int h, int max_len) {
   w.p_hh_bytes = umma_packed_bytes(3 * h, h);
   w.P_hh = take(2 * w.p_hh_bytes / 4);
   w.sync = take(32);
+  w.Xd4 = w.Xd3 = w.P_x4 = w.P_x3 = nullptr;
+  if (dropout) {
+    off = (off + 31) & ~int64_t(31);
+    w.P_x4 = take(umma_packed_bytes(3 * h, 4 * h) / 4);
+    w.P_x3 = take(umma_packed_bytes(3 * h, 3 * h) / 4);
+    w.Xd4 = take(S * 4 * h);
+    w.Xd3 = take(S * 3 * h);
+  }
   w.total_floats = off;
   return w;
 }
@@ -143,14 +240,20 @@ constexpr int kMaxLenWs = 16;  // workspace is sized for sequences up to this lo
 
 }  // namespace
 
-int64_t gru_workspace_floats(int64_t S, int64_t Q, int64_t T, int h) {
-  return carve(nullptr, S, Q, T, h, kMaxLenWs).total_floats;
+int64_t gru_workspace_floats(int64_t S, int64_t Q, int64_t T, int h, bool dropout) {
+  return carve(nullptr, S, Q, T, h, kMaxLenWs, dropout).total_floats;
 }
 
 int launch_gru_recur(const float* GI, const float* PQ, const float* PT, const float* bhh, const int32_t* row_glob,
                      const int32_t* seq_start, const int32_t* seq_len, const float* w_hh4, const float* w_hh3, float* Hs,
                      float* GH, float* hn4, float* hn3, unsigned int* barrier_counter, const int32_t* host_batch_sizes,
                      int max_len, int64_t Q, int h, cudaStream_t stream);
+
+int launch_dropout_mask(uint64_t seed, uint64_t offset, int64_t n, float p, float* out, cudaStream_t stream) {
+  dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(seed, offset, n, p, out);
+  RENET_CHECK_LAUNCH("dropout_mask_kernel");
+  return RENET_OK;
+}
 
 int launch_pack_inputs(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
                        const float* ent, const float* rel, const int32_t* row_seq, const int32_t* seq_s,
@@ -168,12 +271,14 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
                    const int32_t* seq_len, const int32_t* seq_start, const int32_t* host_batch_sizes,
                    int max_len, const float* w_ih4, const float* w_hh4, const float* b_ih4, const float* b_hh4,
                    const float* w_ih3, const float* w_hh3, const float* b_ih3, const float* b_hh3, float* hn4,
-                   float* hn3, int64_t S, int64_t Q, int64_t T, int h, float* ws_base, cudaStream_t stream) {
+                   float* hn3, int64_t S, int64_t Q, int64_t T, int h, float* ws_base, cudaStream_t stream, float p_drop,
+                   uint64_t seed, const int32_t* row_seq) {
   if (max_len > kMaxLenWs) {
     set_error("renet_gru_fwd: max_len %d exceeds the supported %d", max_len, kMaxLenWs);
     return RENET_ERR_INVALID_ARG;
   }
-  GruWs w = carve(ws_base, S, Q, T, h, kMaxLenWs);
+  const bool dropout = p_drop > 0.f;
+  GruWs w = carve(ws_base, S, Q, T, h, kMaxLenWs, dropout);
   const dim3 tb(32, 8);
   auto pack = [&](const float* src, int ld_src, int src_off, float* dst, int ld_dst, int dst_off) -> int {
     dim3 grid((3 * h + 31) / 32, (h + 31) / 32);
@@ -217,10 +322,24 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
     RENET_CHECK_LAUNCH("concat_bias_kernel");
     concat_bias_kernel<<<(6 * h + 255) / 256, 256, 0, stream>>>(b_hh4, b_hh3, w.bhh, 3 * h);
     RENET_CHECK_LAUNCH("concat_bias_kernel");
+    if (dropout) {
+      // masked inputs materialised once, projected by two GEMMs: GI = [X4d @ W_ih4^T | X3d @ W_ih3^T]; PQ = b_ih, PT = 0
+      if ((rc = umma_pack_b(w_ih4, 1, 4 * h, 3 * h, 4 * h, w.P_x4, 0, stream))) return rc;
+      if ((rc = umma_pack_b(w_ih3, 1, 3 * h, 3 * h, 3 * h, w.P_x3, 0, stream))) return rc;
+      pack_inputs_dropout_kernel<<<(unsigned)S, 128, 0, stream>>>(H2, readout, row_glob, glob, ent, rel, row_seq, seq_s, seq_r,
+                                                                 w.Xd4, w.Xd3, S, h, p_drop, seed);
+      RENET_CHECK_LAUNCH("pack_inputs_dropout_kernel");
+      if ((rc = umma_gemm_prepacked(w.Xd4, nullptr, 4 * h, w.P_x4, w.GI, 6 * h, nullptr, S, 3 * h, 4 * h, false, 1, 0, 0, 0, stream))) return rc;
+      if ((rc = umma_gemm_prepacked(w.Xd3, nullptr, 3 * h, w.P_x3, w.GI + 3 * h, 6 * h, nullptr, S, 3 * h, 3 * h, false, 1, 0, 0, 0, stream))) return rc;
+      fill_rows_kernel<<<(unsigned)((Q * 6 * h + 255) / 256), 256, 0, stream>>>(w.bih, w.PQ, Q, 6 * h);
+      RENET_CHECK_LAUNCH("fill_rows_kernel");
+      RENET_CHECK_CUDA(cudaMemsetAsync(w.PT, 0, T * 6 * h * sizeof(float), stream));
+    } else {
     if ((rc = umma_gemm_prepacked(H2, readout, h, w.P_row, w.GI, 6 * h, nullptr, S, 6 * h, h, false, 1, 0, 0, 0, stream))) return rc;
     if ((rc = umma_gemm_prepacked(ent, seq_s, h, w.P_ent, w.PQ, 6 * h, w.bih, Q, 6 * h, h, false, 1, 0, 0, 0, stream))) return rc;
     if ((rc = umma_gemm_prepacked(rel, seq_r, h, w.P_rel, w.PQ, 6 * h, nullptr, Q, 3 * h, h, true, 1, 0, 0, 0, stream))) return rc;
     if ((rc = umma_gemm_prepacked(glob, nullptr, h, w.P_glob, w.PT, 6 * h, nullptr, T, 6 * h, h, false, 1, 0, 0, 0, stream))) return rc;
+    }
     // recurrence: one persistent cooperative tensor-core kernel for all time steps and both encoders (gru_recur.cu);
     // the step-by-step loop below is the fallback for shapes it does not take
     rc = launch_gru_recur(w.GI, w.PQ, w.PT, w.bhh, row_glob, seq_start, seq_len, w_hh4, w_hh3, w.Hs, w.GH, hn4, hn3,
@@ -245,6 +364,10 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
       RENET_CHECK_LAUNCH("gru_gate_kernel");
     }
     return RENET_OK;
+  }
+  if (dropout) {
+    set_error("renet_gru_fwd_dropout needs the tensor-core GEMM engine (RENET_GEMM=umma) and h %% 4 == 0, 3h %% 200 == 0");
+    return RENET_ERR_INVALID_ARG;
   }
   // column blocks of W_ih: encoder x4 = [row | ent | rel | glob], encoder_r x3 = [row | ent | glob]
   if ((rc = pack(w_ih4, 4 * h, 0, w.Brow, 6 * h, 0))) return rc;
@@ -397,12 +520,12 @@ __global__ void unpack_transpose_add_kernel(const float* __restrict__ src, int l
 }
 
 struct GruBwdWs {
-  float *dGI, *dGH, *dPQ, *dPT, *dHa, *dHb, *dBrow, *dBent, *dBrel, *dBglob, *dWhh, *dRows, *dQ, *dbias, *P_hhT;
+  float *dGI, *dGH, *dPQ, *dPT, *dHa, *dHb, *dBrow, *dBent, *dBrel, *dBglob, *dWhh, *dRows, *dQ, *dbias, *P_hhT, *dX4, *dX3;
   int64_t p_hht_bytes;
   int64_t total_floats;
 };
 
-GruBwdWs carve_bwd(float* base, int64_t S, int64_t Q, int64_t T, int h) {
+GruBwdWs carve_bwd(float* base, int64_t S, int64_t Q, int64_t T, int h, bool dropout = false) {
   GruBwdWs w;
   int64_t off = 0;
   auto take = [&](int64_t n) { float* p = base ? base + off : nullptr; off += align4(n); return p; };
@@ -423,14 +546,19 @@ GruBwdWs carve_bwd(float* base, int64_t S, int64_t Q, int64_t T, int h) {
   off = (off + 31) & ~int64_t(31);                       // 128-byte alignment for the TMA source blocks
   w.p_hht_bytes = umma_packed_bytes(h, 3 * h);
   w.P_hhT = take(2 * w.p_hht_bytes / 4);
+  w.dX4 = w.dX3 = nullptr;
+  if (dropout) {
+    w.dX4 = take(S * 4 * h);
+    w.dX3 = take(S * 3 * h);
+  }
   w.total_floats = off;
   return w;
 }
 
 }  // namespace
 
-int64_t gru_bwd_workspace_floats(int64_t S, int64_t Q, int64_t T, int h) {
-  return carve_bwd(nullptr, S, Q, T, h).total_floats;
+int64_t gru_bwd_workspace_floats(int64_t S, int64_t Q, int64_t T, int h, bool dropout) {
+  return carve_bwd(nullptr, S, Q, T, h, dropout).total_floats;
 }
 
 int launch_scatter_add_rows(const float* src, const int32_t* index, float* dst, int64_t n_rows, int d,
@@ -443,9 +571,11 @@ int launch_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_g
                    const float* dhn4, const float* dhn3, float* dH2, float* d_ent, float* d_rel, float* d_glob,
                    float* dw_ih4, float* dw_hh4, float* db_ih4, float* db_hh4, float* dw_ih3, float* dw_hh3,
                    float* db_ih3, float* db_hh3, int64_t N, int64_t S, int64_t Q, int64_t T, int h,
-                   const float* fwd_ws, float* bwd_ws, cudaStream_t stream) {
-  GruWs f = carve(const_cast<float*>(fwd_ws), S, Q, T, h, kMaxLenWs);
-  GruBwdWs b = carve_bwd(bwd_ws, S, Q, T, h);
+                   const float* fwd_ws, float* bwd_ws, cudaStream_t stream, float p_drop, uint64_t seed,
+                   const int32_t* row_seq) {
+  const bool dropout = p_drop > 0.f;
+  GruWs f = carve(const_cast<float*>(fwd_ws), S, Q, T, h, kMaxLenWs, dropout);
+  GruBwdWs b = carve_bwd(bwd_ws, S, Q, T, h, dropout);
   int rc;
   RENET_CHECK_CUDA(cudaMemsetAsync(b.dbias, 0, 12 * h * sizeof(float), stream));
   RENET_CHECK_CUDA(cudaMemsetAsync(b.dWhh, 0, (int64_t)h * 6 * h * sizeof(float), stream));
@@ -511,6 +641,33 @@ int launch_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_g
     dim3 grid((6 * h + 127) / 128, (unsigned)((S + rpb - 1) / rpb));
     colsum_accum_kernel<<<grid, 128, 0, stream>>>(b.dGI, 6 * h, S, 6 * h, b.dbias, rpb);
     RENET_CHECK_LAUNCH("colsum_accum_kernel");
+  }
+  if (dropout) {
+    // ---- input-dropout path: dW_ih = dGI^T @ Xd (the masked inputs the forward pass kept), dXd = dGI @ W_ih, then the
+    //      masks are regenerated and the gradients scattered to H2 rows / ent / rel / glob -------------------------------------
+    if ((rc = sgemm_tn(b.dGI, nullptr, 6 * h, f.Xd4, 4 * h, dw_ih4, 4 * h, 3 * h, 4 * h, S, true, stream))) return rc;
+    if ((rc = sgemm_tn(b.dGI + 3 * h, nullptr, 6 * h, f.Xd3, 3 * h, dw_ih3, 3 * h, 3 * h, 3 * h, S, true, stream))) return rc;
+    if ((rc = sgemm_nn(b.dGI, nullptr, 6 * h, w_ih4, 4 * h, b.dX4, 4 * h, nullptr, S, 4 * h, 3 * h, false, stream))) return rc;
+    if ((rc = sgemm_nn(b.dGI + 3 * h, nullptr, 6 * h, w_ih3, 3 * h, b.dX3, 3 * h, nullptr, S, 3 * h, 3 * h, false, stream))) return rc;
+    unpack_inputs_dropout_kernel<<<(unsigned)S, 128, 0, stream>>>(b.dX4, b.dX3, readout, row_glob, row_seq, seq_s, seq_r, dH2,
+                                                                 d_ent, d_rel, d_glob, S, h, p_drop, seed);
+    RENET_CHECK_LAUNCH("unpack_inputs_dropout_kernel");
+    const dim3 tbd(32, 8);
+    auto unpack_hh = [&](const float* src, int src_off, float* dst) -> int {
+      dim3 grid((3 * h + 31) / 32, (h + 31) / 32);
+      unpack_transpose_add_kernel<<<grid, tbd, 0, stream>>>(src, 6 * h, src_off, 3 * h, dst, h, 0, h);
+      RENET_CHECK_LAUNCH("unpack_transpose_add_kernel");
+      return RENET_OK;
+    };
+    if ((rc = unpack_hh(b.dWhh, 0, dw_hh4))) return rc;
+    if ((rc = unpack_hh(b.dWhh, 3 * h, dw_hh3))) return rc;
+    float* outs[4] = {db_ih4, db_ih3, db_hh4, db_hh3};
+    for (int k = 0; k < 4; ++k) {
+      dim3 grid((3 * h + 127) / 128, 1);
+      colsum_accum_kernel<<<grid, 128, 0, stream>>>(b.dbias + (int64_t)k * 3 * h, 3 * h, 1, 3 * h, outs[k], 1);
+      RENET_CHECK_LAUNCH("colsum_accum_kernel");
+    }
+    return RENET_OK;
   }
   // ---- per-sequence and per-timestamp sums of dGI --------------------------------------------------------
   {

@@ -76,10 +76,6 @@ class RENet(RENetInference, nn.Module):
             hist, reverse = o_hist, True
         s_h, s_q, hb = self.aggregator.encode(hist, s, r, self.ent_embeds, rel_embeds, graph_dict,
                                               self.global_emb, reverse, self.encoder, self.encoder_r, triplets=triplets)
-        if self.training and self.aggregator.dropout.p > 0:
-            # the reference drops out the GRU inputs (Aggregator.py:157-158); the fused path has no
-            # materialised input to drop, so training with dropout goes through forward_unfused().
-            raise RuntimeError('fused encode() does not implement input dropout; use dropout=0 or forward_unfused')
         idx = hb.sample_order(triplets.device)
         if s_h.shape[0] < len(s):                                         # (the no-autograd path pads by itself)
             pad = torch.zeros(len(s) - s_h.shape[0], self.h_dim, device=s_h.device)
@@ -96,13 +92,14 @@ class RENet(RENetInference, nn.Module):
         return loss_sub + 0.1 * loss_sub_r
 
     def forward(self, triplets, s_hist, o_hist, graph_dict, subject=True):
-        if self.training and self.aggregator.dropout.p > 0:
-            return self.forward_unfused(triplets, s_hist, o_hist, graph_dict, subject)
+        """model.py:64-104.  With dropout > 0 in training the three dropout sites of the reference are active: the self-loop
+        message of both RGCN layers (RGCN.py:36-37), the GRU inputs (Aggregator.py:157-158, inside the fused GRU path with
+        Philox masks) and the decoder inputs (model.py:90,99)."""
         return self.decode_loss(*self.encode(triplets, s_hist, o_hist, graph_dict, subject))
 
     def forward_unfused(self, triplets, s_hist, o_hist, graph_dict, subject=True):
-        """Literal model.py:64-104 flow: aggregator -> PackedSequence -> nn.GRU modules.  Used when
-        input dropout is active (training with dropout > 0) and as an API-compatibility path."""
+        """Literal model.py:64-104 flow: aggregator -> PackedSequence -> nn.GRU modules (cuDNN).  An API-compatibility /
+        cross-check path only; ``forward`` never routes here."""
         if subject:
             rel_embeds = self.rel_embeds[:self.num_rels]
             s, r, o = triplets[:, 0], triplets[:, 1], triplets[:, 2]
