@@ -314,16 +314,23 @@ def train_region(args, tkg, pool, global_emb, dev, world, torch, dist):
         phases += [ev[k].elapsed_time(ev[k + 1]) for k in range(4)]
     phases /= len(evs)
     t = torch.tensor([ms, float(msgs)] + list(phases), device=dev, dtype=torch.float64)
+    exposed_min = float(phases[2])
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        tmin = t.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         ms, msgs = tmax[0].item(), tsum[1].item()
         phases = tmax[2:].cpu().numpy()
+        exposed_min = tmin[4].item()
     loss = float(torch.stack(losses).mean())
     tr.close()
     return {'value': msgs / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / args.steps, 'steps': args.steps, 'warmup': warm,
             'forward_ms': float(phases[0]), 'backward_ms': float(phases[1]), 'allreduce_exposed_ms': float(phases[2]),
-            'optimizer_ms': float(phases[3]), 'global_batch': BATCH * world, 'dropout': args.dropout,
+            'optimizer_ms': float(phases[3]), 'allreduce_exposed_min_over_ranks_ms': exposed_min,
+            'note': 'phase times are CUDA-event spans on the compute stream, max over ranks; the exposed all-reduce of the slowest-'
+                    'waiting rank includes the time it waits for the LAST rank to reach the collective (rank skew), the min over '
+                    'ranks is the communication that no rank could hide',
+            'global_batch': BATCH * world, 'dropout': args.dropout,
             'grad_bytes_allreduced_per_step': int(tr.total * 4) if world > 1 else 0, 'buckets': len(tr.buckets),
             'collective': ('nccl all_reduce(sum) of the flat fp32 gradient in %d buckets, launched from autograd hooks during '
                            'backward' % len(tr.buckets)) if world > 1 else 'none (1 GPU)',
