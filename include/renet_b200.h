@@ -401,6 +401,24 @@ int renet_readout_subgraph(const int32_t* readout, int64_t S, int64_t N,
                            float* norm2, int32_t* counts, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Decoder: logits = X @ W^T + bias followed by cross-entropy (reference model.py:89-91: object prediction, X = [ent[s] |
+ * s_h | rel[r]] [B,3h], W = linear.weight [|E|,3h]; model.py:97-100: relation prediction, [B,2h] x [R,2h]).
+ *   renet_decoder_ce_fwd : loss_rows[i] = logsumexp_c(logits[i,c]) - logits[i,target[i]], lse[i] = the logsumexp (kept for
+ *       backward).  tcgen05 3xTF32 GEMM with a fused epilogue: the [B,|E|] logits never reach memory.
+ *   renet_decoder_ce_bwd : for loss = scale * d_scale[0] * sum_i loss_rows[i] (the reference's mean: scale = 1/B; d_scale =
+ *       optional DEVICE scalar, the upstream gradient, so that autograd needs no host read): dX [M,K] written; dW [N,K] and dbias [N] (may be NULL) ACCUMULATED.  The logits are recomputed; the
+ *       gradient of the logits (M x N floats, row-major and transposed) lives in the workspace only.
+ * K % 4 == 0; N is arbitrary (23033 classes).  X [M,K], W [N,K] row-major, 16-byte aligned; target int32 [M].
+ * ---------------------------------------------------------------------------------------------- */
+int64_t renet_decoder_ce_workspace_bytes(int64_t M, int32_t N, int32_t K);
+int renet_decoder_ce_fwd(const float* X, const float* W, const float* bias, const int32_t* target, float* loss_rows,
+                         float* lse, int64_t M, int32_t N, int32_t K, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t renet_decoder_ce_bwd_workspace_bytes(int64_t M, int32_t N, int32_t K);
+int renet_decoder_ce_bwd(const float* X, const float* W, const float* bias, const int32_t* target, const float* lse,
+                         float scale, const float* d_scale, float* dX, float* dW, float* dbias, int64_t M, int32_t N, int32_t K, void* workspace,
+                         int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimiser step of the reference training loop on FLAT fp32 buffers (reference train.py:140-142:
  * torch.nn.utils.clip_grad_norm_(model.parameters(), grad_norm); Adam(lr, weight_decay).step()).  The data-parallel
  * engine keeps all parameters / gradients as views into one flat buffer each (the gradient buffer is what NCCL

@@ -56,6 +56,10 @@ SIGNATURES = {
     'renet_loader_wait': (ctypes.c_int, [_vp, _i64]),
     'renet_prepare_sequences': (ctypes.c_int, [_vp, _i32, _i32, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'renet_pack_inputs': (ctypes.c_int, [_vp] * 12 + [_i64, _i32, _vp]),
+    'renet_decoder_ce_workspace_bytes': (_i64, [_i64, _i32, _i32]),
+    'renet_decoder_ce_fwd': (ctypes.c_int, [_vp] * 6 + [_i64, _i32, _i32, _vp, _i64, _vp]),
+    'renet_decoder_ce_bwd_workspace_bytes': (_i64, [_i64, _i32, _i32]),
+    'renet_decoder_ce_bwd': (ctypes.c_int, [_vp] * 5 + [ctypes.c_float] + [_vp] * 4 + [_i64, _i32, _i32, _vp, _i64, _vp]),
     'renet_grad_sumsq_workspace_bytes': (_i64, []),
     'renet_grad_sumsq': (ctypes.c_int, [_vp, _i64, _vp, _i32, _vp, _i64, _vp]),
     'renet_adam_step': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64] + [ctypes.c_float] * 5 + [_i64, _vp, ctypes.c_float, ctypes.c_float, _vp]),

@@ -86,6 +86,22 @@ void set_weight_generation(int64_t g);
 void* packed_cache_lookup(const void* const* keys, int nkeys, int64_t bytes, bool* hit);
 bool umma_shape_ok(int N, int K);
 int umma_pack_b(const float* B, int64_t sk, int64_t sn, int N, int K, void* Bp, int tile_offset, cudaStream_t stream);
+// fused epilogues of the packed tcgen05 GEMM (umma_gemm.cu): see the comment there
+struct EpiArgs {
+  const int32_t* target;   // [M] class of every row
+  const float* lse;        // [M] (EPI 2)
+  float* pmax;             // [2 * n_tiles, M] (EPI 1)
+  float* psum;             // [2 * n_tiles, M] (EPI 1)
+  float* tlogit;           // [M] (EPI 1): written by the one thread that sees the target column
+  float* dT;               // [N, ldT] (EPI 2): the same gradient transposed (A operand of dW = dlogits^T @ X)
+  int64_t ldT;
+  float scale;             // (EPI 2)
+  const float* dscale;     // (EPI 2) optional device scalar multiplied into scale (the upstream gradient, no host read)
+};
+int umma_gemm_prepacked_ex(const float* A, const int32_t* a_index, int64_t lda, const void* Bp, float* C, int64_t ldc,
+                           const float* bias, int64_t M, int N, int K, bool accumulate, int batch, int64_t batch_a,
+                           int64_t batch_bp, int64_t batch_c, int epi_mode, const EpiArgs& epi, int k_splits, int64_t split_c,
+                           cudaStream_t stream);
 int umma_gemm_prepacked(const float* A, const int32_t* a_index, int64_t lda, const void* Bp, float* C, int64_t ldc,
                         const float* bias, int64_t M, int N, int K, bool accumulate, int batch, int64_t batch_a,
                         int64_t batch_bp, int64_t batch_c, cudaStream_t stream);

@@ -253,23 +253,37 @@ umma_pack_b_kernel(const float* __restrict__ B, int64_t sk, int64_t sn, int N, i
   }
 }
 
+// Fused-epilogue modes of the packed kernel (the decoder of model.py:89-91,97-100: logits = X @ W^T + b, cross-entropy):
+//   EPI 0  C = acc (+bias) (+C)                                   -- plain GEMM
+//   EPI 1  per (row, half column tile): running max and sum of exp of the logits, and the target's logit -- the
+//          [M, N] logits never reach memory; ce_reduce_kernel turns the partials into logsumexp and the loss
+//   EPI 2  dlogits[row, col] = (exp(logit - lse[row]) - [col == target[row]]) * scale, written to memory for the two
+//          gradient GEMMs (the backward pass recomputes the logits instead of keeping them)
+
 // One CTA = a PAIR of 128-row tiles sharing every B block: the packed B chunk (53 KB) is fetched once per pair,
 // the two tiles' A buffers ping-pong (tile 1's chunk is staged while tile 0's MMAs run and vice versa), and the
 // two accumulators live side by side in TMEM (2 x 256 columns).
-template <bool INDEXED>
+template <bool INDEXED, int EPI = 0>
 __global__ void __launch_bounds__(UTHREADS, 1)
 umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__ a_index, int64_t lda,
                         const uint8_t* __restrict__ Bp, float* __restrict__ C, int64_t ldc,
                         const float* __restrict__ bias, int64_t M, int N, int K, int n_chunks, int accumulate,
-                        int64_t batch_a, int64_t batch_bp, int64_t batch_c) {
+                        int64_t batch_a, int64_t batch_bp, int64_t batch_c, EpiArgs epi, int k_splits, int64_t split_c) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);     // swizzle atoms need 1024-byte alignment
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  A += blockIdx.z * batch_a;            // batched GEMMs (the two GRU encoders): per-batch operand offsets
-  Bp += blockIdx.z * batch_bp;
-  C += blockIdx.z * batch_c;
-  if (bias != nullptr) bias += blockIdx.z * (int64_t)N;
+  // grid.z = batch x K-split.  Batched GEMMs (the two GRU encoders): per-batch operand offsets.  Split-K (long-K,
+  // few-tile products such as dX = dlogits @ W of the decoder): split s owns the chunks [s*cps, (s+1)*cps) and writes its
+  // partial product to C + s*split_c; the caller sums the partials.
+  const int zb = blockIdx.z / k_splits, split = blockIdx.z - zb * k_splits;
+  A += zb * batch_a;
+  Bp += zb * batch_bp;
+  C += zb * batch_c + (int64_t)split * split_c;
+  if (bias != nullptr) bias += zb * (int64_t)N;
+  const int cps = (n_chunks + k_splits - 1) / k_splits;
+  const int c_begin = split * cps;
+  const int n_local = min(cps, n_chunks - c_begin);      // >= 1: the launcher never creates an empty split
   const int64_t row_base = (int64_t)blockIdx.x * (2 * UM);
   const int nt = blockIdx.y;
   const int n0 = nt * UN;
@@ -321,7 +335,7 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
   const uint8_t* bp_tile = Bp + (size_t)nt * n_chunks * P_B_CHUNK;
   float4 vnext[4];
   auto load_a = [&](int tl, int c) {
-    const int k0 = c * P_BK;
+    const int k0 = (c_begin + c) * P_BK;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       vnext[t] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -329,7 +343,7 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
     }
   };
   load_a(0, 0);
-  for (int c = 0; c < n_chunks; ++c) {
+  for (int c = 0; c < n_local; ++c) {
     const int bs = c & 1;
     if (tid == 0) {   // TMA: one bulk copy per chunk brings the packed B block for BOTH tiles
       if (c >= 2) mbar_wait(bar0 + 16 + 8 * bs, ((c >> 1) - 1) & 1);          // both tiles' MMAs of chunk c-2 done
@@ -337,7 +351,7 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
       const uint32_t dstB = smem_base + 4 * P_A_BYTES + bs * P_B_CHUNK;
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)P_B_CHUNK) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dstB),
-                   "l"(bp_tile + (size_t)c * P_B_CHUNK), "r"((uint32_t)P_B_CHUNK), "r"(full)
+                   "l"(bp_tile + (size_t)(c_begin + c) * P_B_CHUNK), "r"((uint32_t)P_B_CHUNK), "r"(full)
                    : "memory");
     }
 #pragma unroll
@@ -349,7 +363,7 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
 #pragma unroll
       for (int t = 0; t < 4; ++t) v[t] = vnext[t];
       if (tl == 0) load_a(1, c);                                              // next step's global loads fly during this step
-      else if (c + 1 < n_chunks) load_a(0, c + 1);
+      else if (c + 1 < n_local) load_a(0, c + 1);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         float4 hi, lo;
@@ -378,7 +392,7 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
         umma_commit(bar0 + 32 + 8 * tl);                     // A_tl may be overwritten
         if (tl == 1) {
           umma_commit(bar0 + 16 + 8 * bs);                   // B stage may be overwritten
-          if (c == n_chunks - 1) umma_commit(bar0 + 48);     // both accumulators complete
+          if (c == n_local - 1) umma_commit(bar0 + 48);      // both accumulators complete
         }
       }
     }
@@ -395,11 +409,49 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
     for (int tl = 0; tl < 2; ++tl) {
       const int64_t gr = row_base + tl * UM + r;
       const uint32_t taddr = tmem_base + tl * 256 + ((uint32_t)(q * 32) << 16);
+      // EPI 1 state of this thread's (row, half tile): running max / sum of exp; EPI 2: the row's logsumexp and target
+      float run_m = -3.0e38f, run_s = 0.f;
+      const int tgt = (EPI != 0 && gr < M) ? __ldg(epi.target + gr) : -1;
+      const float row_lse = (EPI == 2 && gr < M) ? __ldg(epi.lse + gr) : 0.f;
+      const float gscale = (EPI == 2) ? epi.scale * (epi.dscale != nullptr ? __ldg(epi.dscale) : 1.f) : 0.f;
       auto emit8 = [&](const uint32_t* v8, int cc) {
         if (gr < M && cc < tile_n) {
           float o[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v8[i]);
+          if (EPI != 0) {
+            // fused cross-entropy epilogues: columns are guarded one by one (the class count need not be a multiple of 8)
+            const int nv = min(8, tile_n - cc);
+            float mx = -3.0e38f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (i < nv) {
+                if (bias != nullptr) o[i] += __ldg(bias + n0 + cc + i);
+                mx = fmaxf(mx, o[i]);
+              }
+            if (EPI == 1) {
+              const float nm = fmaxf(run_m, mx);
+              float add = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (i < nv) {
+                  add += expf(o[i] - nm);
+                  if (n0 + cc + i == tgt) epi.tlogit[gr] = o[i];
+                }
+              run_s = run_s * expf(run_m - nm) + add;
+              run_m = nm;
+            } else {
+              float* dp = C + gr * ldc + n0 + cc;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (i < nv) {
+                  const float gv = (expf(o[i] - row_lse) - (n0 + cc + i == tgt ? 1.f : 0.f)) * gscale;
+                  dp[i] = gv;                                              // row-major: A of dX = dlogits @ W
+                  epi.dT[(int64_t)(n0 + cc + i) * epi.ldT + gr] = gv;      // transposed (lanes = consecutive rows: coalesced)
+                }
+            }
+            return;
+          }
           float* cp = C + gr * ldc + n0 + cc;
           if (bias != nullptr) {
             const float4 b0 = ldg_f4(bias + n0 + cc), b1 = ldg_f4(bias + n0 + cc + 4);
@@ -439,6 +491,11 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
                      : "r"(taddr + (uint32_t)cc));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         emit8(v8, cc);
+      }
+      if (EPI == 1 && gr < M) {
+        const int64_t pi = (int64_t)(nt * 2 + half) * M + gr;
+        epi.pmax[pi] = run_m;
+        epi.psum[pi] = run_s;
       }
     }
   }
@@ -523,26 +580,45 @@ int umma_pack_b(const float* B, int64_t sk, int64_t sn, int N, int K, void* Bp, 
 }
 
 // C[b] (+)= A[b] @ Bpacked[b] (+bias[b]) for b < batch; strides in elements (A, C) / bytes (Bp).
-int umma_gemm_prepacked(const float* A, const int32_t* a_index, int64_t lda, const void* Bp, float* C, int64_t ldc,
-                        const float* bias, int64_t M, int N, int K, bool accumulate, int batch, int64_t batch_a,
-                        int64_t batch_bp, int64_t batch_c, cudaStream_t stream) {
+// epi_mode 1 / 2: fused cross-entropy epilogues (EpiArgs); k_splits > 1: split-K partial products at C + s*split_c.
+int umma_gemm_prepacked_ex(const float* A, const int32_t* a_index, int64_t lda, const void* Bp, float* C, int64_t ldc,
+                           const float* bias, int64_t M, int N, int K, bool accumulate, int batch, int64_t batch_a,
+                           int64_t batch_bp, int64_t batch_c, int epi_mode, const EpiArgs& epi, int k_splits, int64_t split_c,
+                           cudaStream_t stream) {
   if (M <= 0) return RENET_OK;
   static bool attr2 = false;
   if (!attr2) {
-    RENET_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
-    RENET_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+    RENET_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_packed_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+    RENET_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_packed_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+    RENET_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_packed_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+    RENET_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_packed_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
     attr2 = true;
   }
   const int n_tiles = (N + UN - 1) / UN, n_chunks = (K + P_BK - 1) / P_BK;
-  dim3 grid((unsigned)((M + 2 * UM - 1) / (2 * UM)), (unsigned)n_tiles, (unsigned)batch);
-  if (a_index)
-    umma_gemm_packed_kernel<true><<<grid, UTHREADS, P_SMEM, stream>>>(A, a_index, lda, (const uint8_t*)Bp, C, ldc, bias, M, N, K,
-                                                                    n_chunks, accumulate, batch_a, batch_bp, batch_c);
-  else
-    umma_gemm_packed_kernel<false><<<grid, UTHREADS, P_SMEM, stream>>>(A, a_index, lda, (const uint8_t*)Bp, C, ldc, bias, M, N, K,
-                                                                     n_chunks, accumulate, batch_a, batch_bp, batch_c);
+  if (k_splits < 1) k_splits = 1;
+  if (k_splits > n_chunks) k_splits = n_chunks;
+  while (k_splits > 1 && ((n_chunks + k_splits - 1) / k_splits) * (k_splits - 1) >= n_chunks) --k_splits;   // no empty split
+  dim3 grid((unsigned)((M + 2 * UM - 1) / (2 * UM)), (unsigned)n_tiles, (unsigned)(batch * k_splits));
+#define RENET_UMMA_LAUNCH(IDX, EP)                                                                                       \
+  umma_gemm_packed_kernel<IDX, EP><<<grid, UTHREADS, P_SMEM, stream>>>(A, a_index, lda, (const uint8_t*)Bp, C, ldc, bias, M, N, K, \
+                                                                      n_chunks, accumulate, batch_a, batch_bp, batch_c, epi,  \
+                                                                      k_splits, split_c)
+  if (epi_mode == 1) RENET_UMMA_LAUNCH(false, 1);
+  else if (epi_mode == 2) RENET_UMMA_LAUNCH(false, 2);
+  else if (a_index) RENET_UMMA_LAUNCH(true, 0);
+  else RENET_UMMA_LAUNCH(false, 0);
+#undef RENET_UMMA_LAUNCH
   RENET_CHECK_LAUNCH("umma_gemm_packed_kernel");
-  return RENET_OK;
+  return k_splits;      // > 0: the number of K-splits actually used (1 = C holds the result)
+}
+
+int umma_gemm_prepacked(const float* A, const int32_t* a_index, int64_t lda, const void* Bp, float* C, int64_t ldc,
+                        const float* bias, int64_t M, int N, int K, bool accumulate, int batch, int64_t batch_a,
+                        int64_t batch_bp, int64_t batch_c, cudaStream_t stream) {
+  EpiArgs none{};
+  const int r = umma_gemm_prepacked_ex(A, a_index, lda, Bp, C, ldc, bias, M, N, K, accumulate, batch, batch_a, batch_bp, batch_c,
+                                       0, none, 1, 0, stream);
+  return r < 0 ? r : RENET_OK;
 }
 
 int umma_gemm_nn_try(const float* A, const int32_t* a_index, int64_t lda, const float* B, int64_t ldb, float* C,

@@ -5,7 +5,7 @@ Constructor signature, attribute and parameter names (``ent_embeds``, ``rel_embe
 reference's, so a reference checkpoint's ``state_dict`` loads as is.  ``forward(triplets, s_hist,
 o_hist, graph_dict, subject=True) -> loss`` follows model.py:64-104: direction select, sort by
 history length, RGCN aggregate, GRU final hidden, zero rows for empty histories, the two linear
-decoders + cross-entropy (decoders stay PyTorch: SURVEY.md section 8(f) row 3).
+decoders + cross-entropy (fused on the tcgen05 engine, decoder.py: SURVEY.md section 8(f) row 3).
 
 The test-time autoregressive routines (model.py:107-446: ``init_history``, ``pred_r_rank2``,
 ``predict``, ``evaluate``, ``evaluate_filter``, ``update_cache``) come from ``inference.RENetInference``
@@ -85,10 +85,11 @@ class RENet(RENetInference, nn.Module):
 
     def decode_loss(self, s, r, o, s_h, s_q, rel_embeds):
         """model.py:89-91, 97-103."""
-        ob_pred = self.linear(self.dropout(torch.cat((self.ent_embeds[s], s_h, rel_embeds[r]), dim=1)))
-        loss_sub = self.criterion(ob_pred, o)
-        ob_pred_r = self.linear_r(self.dropout(torch.cat((self.ent_embeds[s], s_q), dim=1)))
-        loss_sub_r = self.criterion(ob_pred_r, r)
+        from .decoder import decoder_cross_entropy
+        x = self.dropout(torch.cat((self.ent_embeds[s], s_h, rel_embeds[r]), dim=1))
+        loss_sub = decoder_cross_entropy(x, self.linear.weight, self.linear.bias, o)           # fused logits + CE
+        x_r = self.dropout(torch.cat((self.ent_embeds[s], s_q), dim=1))
+        loss_sub_r = decoder_cross_entropy(x_r, self.linear_r.weight, self.linear_r.bias, r)
         return loss_sub + 0.1 * loss_sub_r
 
     def forward(self, triplets, s_hist, o_hist, graph_dict, subject=True):
