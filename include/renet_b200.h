@@ -252,6 +252,36 @@ int renet_gru_bwd_dropout(const float* H2, const int32_t* readout, const int32_t
                           const void* fwd_workspace, void* bwd_workspace, int64_t bwd_workspace_bytes, void* stream);
 int renet_dropout_mask(uint64_t seed, uint64_t offset, int64_t n, float p, float* out, void* stream);
 
+/* GRU(s) on caller-materialised inputs, final hidden states only: X4 [S,k4] for `encoder`-style weights w_ih4 [3h,k4],
+ * optionally X3 [S,k3] for a second GRU run in the same launches (NULL = a single GRU: the reference's global model
+ * nn.GRU(h_dim, h_dim), global_model.py:25,49; hn3 / the *_3 gradients are then scratch / NULL).  Rows are sequence-major
+ * (sequence q owns rows seq_start[q] .. +seq_len[q]-1), sequences sorted by length descending, h0 = 0.  Input projection =
+ * two tensor-core GEMMs, recurrence = the kernel of renet_gru_fwd.  k4 <= 4h, k3 <= 3h, multiples of 4.  Workspaces:
+ * renet_gru_dropout_workspace_bytes(S, Q, 1, h) / renet_gru_bwd_dropout_workspace_bytes(S, Q, 1, h).
+ * Backward: dX4 [S,k4] (dX3) written, parameter gradients accumulated. */
+int renet_gru_dense_fwd(const float* X4, int32_t k4, const float* X3, int32_t k3, const int32_t* seq_len,
+                        const int32_t* seq_start, const int32_t* host_batch_sizes, int32_t max_len,
+                        const float* w_ih4, const float* w_hh4, const float* b_ih4, const float* b_hh4,
+                        const float* w_ih3, const float* w_hh3, const float* b_ih3, const float* b_hh3,
+                        float* hn4, float* hn3, int64_t S, int64_t Q, int32_t h,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+int renet_gru_dense_bwd(const float* X4, int32_t k4, const float* X3, int32_t k3, const int32_t* seq_len,
+                        const int32_t* seq_start, const int32_t* host_batch_sizes, int32_t max_len,
+                        const float* w_ih4, const float* w_hh4, const float* w_ih3, const float* w_hh3,
+                        const float* dhn4, const float* dhn3, float* dX4, float* dX3,
+                        float* dw_ih4, float* dw_hh4, float* db_ih4, float* db_hh4,
+                        float* dw_ih3, float* dw_hh3, float* db_ih3, float* db_hh3,
+                        int64_t S, int64_t Q, int32_t h, const void* fwd_workspace, void* bwd_workspace,
+                        int64_t bwd_workspace_bytes, void* stream);
+
+/* Per-graph pooling over a batched graph: out[g] = max (mode 1) or mean (mode 0) of H[seg_ptr[g] .. seg_ptr[g+1]) -- dgl.max_nodes /
+ * dgl.mean_nodes of the reference's global aggregator (Aggregator.py:58-61).  argmax [G,d] (mode 1) keeps the winning row for
+ * backward; renet_segment_pool_bwd writes dH [N,d] (zeros elsewhere). */
+int renet_segment_pool_fwd(const float* H, const int32_t* seg_ptr, int64_t G, int32_t d, int32_t mode, float* out,
+                           int32_t* argmax, void* stream);
+int renet_segment_pool_bwd(const float* dout, const int32_t* seg_ptr, const int32_t* argmax, int64_t G, int64_t N,
+                           int32_t d, int32_t mode, float* dH, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * HOST-side batching of history graphs (no CUDA; every pointer here is a HOST pointer).  Replaces
  * utils.get_sorted_s_r_embed_rgcn / get_s_r_embed_rgcn minus the embedding lookups (utils.py:209-283):

@@ -419,6 +419,55 @@ def gen_aggregator_predict(ns):
     print('aggregator_predict.npz:', len(blob), 'arrays')
 
 
+def gen_global_tiny(ns):
+    """RENet_global (global_model.py) run by the unmodified reference on the tiny stream: training loss + gradients for a
+    batch of timestamps (both directions, max and mean pooling), predict() at one time, and get_global_emb() -- the
+    vectors the hot path consumes as global_emb[t].  h = 200 because the reference hard-codes num_bases = 100."""
+    tiny = np.load(os.path.join(OUT, 'renet_tiny.npz'))
+    quads = tiny['quads'].astype(np.int64)
+    num_e, R, h, seed = int(tiny['num_e']), int(tiny['R']), 200, 21
+    times = np.unique(quads[:, 3])
+    blob = {'h': h, 'seed': seed, 'times': times}
+    with ref_loader.cpu_patches():
+        gd = {}
+        for t in times:
+            gd[int(t)] = ns.utils.get_big_graph(quads[quads[:, 3] == t][:, :3], R)
+        tps, tpo = ns.utils.get_true_distribution(quads, num_e)
+        blob['true_prob_s'], blob['true_prob_o'] = tps, tpo
+        for pool in (1, 0):
+            m = ns.global_model.RENet_global(num_e, h, R, dropout=0, model=3, seq_len=10, num_k=10, maxpool=pool)
+            shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+            m.load_state_dict(det_params(shapes, seed), strict=True)
+            if pool == 1:
+                blob['shapes_keys'] = np.asarray(sorted(shapes))
+                blob['shapes_vals'] = np.asarray([list(shapes[k]) + [0] * (2 - len(shapes[k])) for k in sorted(shapes)])
+            t_batch = torch.from_numpy(times[[5, 0, 12, 3, 13, 1]])
+            sel = [5, 0, 12, 3, 13, 1]
+            for subj in (True, False):
+                m.zero_grad()
+                loss = m(t_batch, torch.from_numpy(tps[sel]), torch.from_numpy(tpo[sel]), gd, subject=subj)
+                loss.backward()
+                tag = 'pool%d/%s' % (pool, 'subj' if subj else 'obj')
+                blob[tag + '/loss'] = np.float64(loss.item())
+                for k, p in m.named_parameters():
+                    if p.grad is not None:
+                        blob['%s/grad/%s' % (tag, k)] = p.grad.numpy().copy()
+            with torch.no_grad():
+                s_q, sub, prob = m.predict(int(times[7]), gd)
+                blob['pool%d/pred_sq' % pool] = s_q.view(-1).numpy().copy()
+                blob['pool%d/pred_sub' % pool] = sub.view(-1).numpy().copy()
+                if pool == 1:
+                    ge = m.get_global_emb(times, gd)
+                    blob['pool1/global_emb_keys'] = np.asarray(sorted(ge))
+                    blob['pool1/global_emb'] = np.stack([ge[k].view(-1).numpy() for k in sorted(ge)])
+                    packed = m.aggregator(torch.from_numpy(times[[12, 5, 3]]), m.ent_embeds, gd, reverse=False)
+                    blob['pool1/agg_packed'] = packed.data.numpy().copy()
+                    blob['pool1/agg_bs'] = packed.batch_sizes.numpy().copy()
+    blob['t_batch'] = np.asarray([5, 0, 12, 3, 13, 1])
+    np.savez_compressed(os.path.join(OUT, 'global_tiny.npz'), **blob)
+    print('global_tiny.npz: losses', blob['pool1/subj/loss'], blob['pool1/obj/loss'], blob['pool0/subj/loss'])
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
@@ -429,3 +478,4 @@ if __name__ == '__main__':
     gen_renet_icews18_slice(ns)
     gen_renet_eval_tiny(ns)
     gen_aggregator_predict(ns)
+    gen_global_tiny(ns)

@@ -21,7 +21,7 @@ import torch
 
 REFERENCE_DIR = os.environ.get('RENET_REFERENCE_DIR', '/root/reference')
 _SHIM_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'dgl_shim')
-_REF_MODULES = ('utils', 'RGCN', 'Aggregator', 'model')
+_REF_MODULES = ('utils', 'RGCN', 'Aggregator', 'model', 'global_model')
 
 
 def available():

@@ -368,3 +368,80 @@ def renet_forward(params, triplets, hist, hist_t, graph_dict, global_emb, subjec
     loss_sub_r = torch.nn.functional.cross_entropy(ob_pred_r, r_tem)     # model.py:98-100
     return dict(loss=loss_sub + 0.1 * loss_sub_r, s_h=s_h, s_q=s_q, X4=X4, X3=X3, perm=perm,
                 batch_sizes=bs, H0=H0, H1=H1, H2=H2, graph=g, batch=bh, etype=et)
+
+
+# --------------------------------------------------------------------------------------------------
+# global model (global_model.py, Aggregator.RGCNAggregator_global), dropout off
+# --------------------------------------------------------------------------------------------------
+def global_windows(t_list, times, seq_len=10):
+    """Aggregator.py:28-45: t_list sorted descending; zeros (the first timestamp: no past) are dropped; each remaining t
+    owns the <= seq_len graph timestamps before it."""
+    time_unit = times[1] - times[0]
+    out = []
+    for tim in t_list:
+        if int(tim) == 0:
+            continue
+        length = int(tim // time_unit)
+        out.append(list(times[length - seq_len:length]) if seq_len <= length else list(times[:length]))
+    return out
+
+
+def global_pooled(params, window_times, graph_dict, reverse, maxpool, num_bases=100):
+    """Aggregator.py:53-62 / 96-105: dgl.batch of WHOLE graphs, two block layers, max / mean over each graph's nodes."""
+    P = params
+    gs = [graph_dict[int(t)] for t in window_times]
+    off = np.concatenate(([0], np.cumsum([g.number_of_nodes() for g in gs]))).astype(np.int64)
+    src = torch.as_tensor(np.concatenate([g.src + o for g, o in zip(gs, off[:-1])]))
+    dst = torch.as_tensor(np.concatenate([g.dst + o for g, o in zip(gs, off[:-1])]))
+    et = torch.as_tensor(np.concatenate([g.type_o if reverse else g.type_s for g in gs]))
+    norm = torch.as_tensor(np.concatenate([g.norm for g in gs]))
+    H0 = P['ent_embeds'][torch.as_tensor(np.concatenate([g.id for g in gs]))]
+    H1 = rgcn_block_layer(H0, P['aggregator.rgcn1.weight'], P['aggregator.rgcn1.loop_weight'], src, dst, et, norm, True,
+                          num_bases)
+    H2 = rgcn_block_layer(H1, P['aggregator.rgcn2.weight'], P['aggregator.rgcn2.loop_weight'], src, dst, et, norm, False,
+                          num_bases)
+    rows = []
+    for a, b in zip(off[:-1], off[1:]):
+        rows.append(H2[a:b].max(dim=0).values if maxpool == 1 else H2[a:b].mean(dim=0))
+    return torch.stack(rows)
+
+
+def soft_cross_entropy(pred, soft_targets):
+    """utils.py:287-290."""
+    logp = torch.nn.functional.log_softmax(pred.double(), dim=1)
+    return torch.mean(torch.sum(-soft_targets.double() * logp, 1))
+
+
+def global_forward(params, t_list, true_prob_s, true_prob_o, graph_dict, subject, maxpool=1, seq_len=10, num_bases=100):
+    """RENet_global.forward (global_model.py:35-55): loss of one direction for a batch of timestamps."""
+    P = params
+    reverse = not subject
+    lin = 'linear_s' if subject else 'linear_o'
+    true_prob = torch.as_tensor(true_prob_o if subject else true_prob_s)
+    t_host = np.asarray(t_list, dtype=np.int64)
+    idx = np.argsort(-t_host, kind='stable')                                    # global_model.py:45
+    times = list(graph_dict.keys())
+    windows = global_windows(t_host[idx], times, seq_len)
+    uniq = sorted({int(t) for w in windows for t in w})                          # Aggregator.py:47
+    pos = {t: i for i, t in enumerate(uniq)}
+    info = global_pooled(P, uniq, graph_dict, reverse, maxpool, num_bases)
+    X = info[torch.as_tensor([pos[int(t)] for w in windows for t in w], dtype=torch.long)]
+    lens = [len(w) for w in windows]
+    s_q = gru_final_hidden_batched(X, lens, P['encoder_global.weight_ih_l0'], P['encoder_global.weight_hh_l0'],
+                                   P['encoder_global.bias_ih_l0'], P['encoder_global.bias_hh_l0'])
+    s_q = torch.cat((s_q, torch.zeros(len(t_host) - len(s_q), s_q.shape[1])), dim=0)    # global_model.py:51
+    pred = s_q @ P[lin + '.weight'].t() + P[lin + '.bias']
+    return soft_cross_entropy(pred, true_prob[torch.as_tensor(idx)])
+
+
+def global_predict(params, t, graph_dict, subject=True, maxpool=1, seq_len=10, num_bases=100):
+    """RENet_global.predict (global_model.py:77-89): (s_q [h], logits [in_dim]) from the graphs before time t."""
+    P = params
+    times = list(graph_dict.keys())
+    k = sum(1 for tt in times if tt < t)                                         # Aggregator.py:78-82 (times ascend)
+    window = times[k - seq_len:k] if seq_len <= k else times[:k]
+    X = global_pooled(P, window, graph_dict, not subject, maxpool, num_bases)
+    s_q = gru_final_hidden_batched(X, [len(window)], P['encoder_global.weight_ih_l0'], P['encoder_global.weight_hh_l0'],
+                                   P['encoder_global.bias_ih_l0'], P['encoder_global.bias_hh_l0'])[0]
+    lin = 'linear_s' if subject else 'linear_o'
+    return s_q, P[lin + '.weight'] @ s_q + P[lin + '.bias']

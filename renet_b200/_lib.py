@@ -42,6 +42,10 @@ SIGNATURES = {
     'renet_gru_bwd_dropout_workspace_bytes': (_i64, [_i64, _i64, _i64, _i32]),
     'renet_gru_bwd_dropout': (ctypes.c_int, [_vp] * 12 + [_i32] + [_vp] * 18 + [_i64, _i64, _i64, _i64, _i32, ctypes.c_float, ctypes.c_uint64, _vp, _vp, _i64, _vp]),
     'renet_dropout_mask': (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, _i64, ctypes.c_float, _vp, _vp]),
+    'renet_gru_dense_fwd': (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32] + [_vp] * 10 + [_i64, _i64, _i32, _vp, _i64, _vp]),
+    'renet_gru_dense_bwd': (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32] + [_vp] * 16 + [_i64, _i64, _i32, _vp, _vp, _i64, _vp]),
+    'renet_segment_pool_fwd': (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    'renet_segment_pool_bwd': (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     'renet_set_host_threads': (ctypes.c_int, [ctypes.c_int]),
     'renet_host_assemble_batch': (ctypes.c_int, [_i64] + [_vp] * 13 + [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
     'renet_host_plan_batch': (ctypes.c_int, [_i64] + [_vp] * 10 + [_i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp]),

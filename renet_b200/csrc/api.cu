@@ -41,7 +41,8 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
                    int max_len, const float* w_ih4, const float* w_hh4, const float* b_ih4, const float* b_hh4,
                    const float* w_ih3, const float* w_hh3, const float* b_ih3, const float* b_hh3, float* hn4,
                    float* hn3, int64_t S, int64_t Q, int64_t T, int h, float* ws_base, cudaStream_t stream, float p_drop = 0.f,
-                   uint64_t seed = 0, const int32_t* row_seq = nullptr);
+                   uint64_t seed = 0, const int32_t* row_seq = nullptr, const float* ext_X4 = nullptr, int k4 = 0,
+                   const float* ext_X3 = nullptr, int k3 = 0);
 int64_t gru_bwd_workspace_floats(int64_t S, int64_t Q, int64_t T, int h, bool dropout = false);
 int launch_dropout_mask(uint64_t seed, uint64_t offset, int64_t n, float p, float* out, cudaStream_t stream);
 int launch_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
@@ -52,7 +53,8 @@ int launch_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_g
                    float* dw_ih4, float* dw_hh4, float* db_ih4, float* db_hh4, float* dw_ih3, float* dw_hh3,
                    float* db_ih3, float* db_hh3, int64_t N, int64_t S, int64_t Q, int64_t T, int h,
                    const float* fwd_ws, float* bwd_ws, cudaStream_t stream, float p_drop = 0.f, uint64_t seed = 0,
-                   const int32_t* row_seq = nullptr);
+                   const int32_t* row_seq = nullptr, const float* ext_X4 = nullptr, int k4 = 0, const float* ext_X3 = nullptr,
+                   int k3 = 0, float* out_dX4 = nullptr, float* out_dX3 = nullptr);
 int launch_pack_inputs(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
                        const float* ent, const float* rel, const int32_t* row_seq, const int32_t* seq_s,
                        const int32_t* seq_r, const int32_t* packed_row, float* X4, float* X3, int64_t S, int h,
@@ -372,6 +374,43 @@ int renet_gru_bwd_dropout(const float* H2, const int32_t* readout, const int32_t
                         w_hh4, w_ih3, w_hh3, dhn4, dhn3, dH2, d_ent, d_rel, d_glob, dw_ih4, dw_hh4, db_ih4, db_hh4, dw_ih3,
                         dw_hh3, db_ih3, db_hh3, N, S, Q, T, h, (const float*)fwd_workspace, (float*)bwd_workspace,
                         (cudaStream_t)stream, p, seed, row_seq);
+}
+
+int renet_gru_dense_fwd(const float* X4, int32_t k4, const float* X3, int32_t k3, const int32_t* seq_len,
+                        const int32_t* seq_start, const int32_t* host_batch_sizes, int32_t max_len, const float* w_ih4,
+                        const float* w_hh4, const float* b_ih4, const float* b_hh4, const float* w_ih3, const float* w_hh3,
+                        const float* b_ih3, const float* b_hh3, float* hn4, float* hn3, int64_t S, int64_t Q, int32_t h,
+                        void* workspace, int64_t workspace_bytes, void* stream) {
+  RENET_CHECK_ARG(S >= 0 && Q >= 0 && h > 0 && max_len >= 0, "renet_gru_dense_fwd: bad shape");
+  if (S == 0 || Q == 0) return RENET_OK;
+  RENET_CHECK_ARG(X4 && seq_len && seq_start && host_batch_sizes && w_ih4 && w_hh4 && b_ih4 && b_hh4 && hn4 && hn3 && workspace,
+                  "renet_gru_dense_fwd: null pointer");
+  RENET_CHECK_ARG(X3 == nullptr || (w_ih3 && w_hh3 && b_ih3 && b_hh3), "renet_gru_dense_fwd: second encoder needs its weights");
+  RENET_CHECK_ARG(workspace_bytes >= renet_gru_dropout_workspace_bytes(S, Q, 1, h), "renet_gru_dense_fwd: workspace too small");
+  RENET_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 127) == 0, "renet_gru_dense_fwd: workspace must be 128-byte aligned");
+  return launch_gru_fwd(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, seq_len, seq_start,
+                        host_batch_sizes, max_len, w_ih4, w_hh4, b_ih4, b_hh4, w_ih3, w_hh3, b_ih3, b_hh3, hn4, hn3, S, Q, 1, h,
+                        (float*)workspace, (cudaStream_t)stream, 0.f, 0, nullptr, X4, k4, X3, k3);
+}
+
+int renet_gru_dense_bwd(const float* X4, int32_t k4, const float* X3, int32_t k3, const int32_t* seq_len,
+                        const int32_t* seq_start, const int32_t* host_batch_sizes, int32_t max_len, const float* w_ih4,
+                        const float* w_hh4, const float* w_ih3, const float* w_hh3, const float* dhn4, const float* dhn3,
+                        float* dX4, float* dX3, float* dw_ih4, float* dw_hh4, float* db_ih4, float* db_hh4, float* dw_ih3,
+                        float* dw_hh3, float* db_ih3, float* db_hh3, int64_t S, int64_t Q, int32_t h,
+                        const void* fwd_workspace, void* bwd_workspace, int64_t bwd_workspace_bytes, void* stream) {
+  RENET_CHECK_ARG(S >= 0 && Q >= 0 && h > 0 && max_len >= 0, "renet_gru_dense_bwd: bad shape");
+  if (S == 0 || Q == 0) return RENET_OK;
+  RENET_CHECK_ARG(X4 && seq_len && seq_start && host_batch_sizes && w_ih4 && w_hh4 && dhn4 && dhn3 && dX4 && dw_ih4 && dw_hh4 &&
+                      db_ih4 && db_hh4 && fwd_workspace && bwd_workspace, "renet_gru_dense_bwd: null pointer");
+  RENET_CHECK_ARG(X3 == nullptr || (w_ih3 && w_hh3 && dX3 && dw_ih3 && dw_hh3 && db_ih3 && db_hh3),
+                  "renet_gru_dense_bwd: second encoder needs its weights and gradient buffers");
+  RENET_CHECK_ARG(bwd_workspace_bytes >= renet_gru_bwd_dropout_workspace_bytes(S, Q, 1, h), "renet_gru_dense_bwd: workspace too small");
+  return launch_gru_bwd(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, seq_len, seq_start,
+                        host_batch_sizes, max_len, w_ih4, w_hh4, w_ih3, w_hh3, dhn4, dhn3, nullptr, nullptr, nullptr, nullptr,
+                        dw_ih4, dw_hh4, db_ih4, db_hh4, dw_ih3, dw_hh3, db_ih3, db_hh3, 0, S, Q, 1, h,
+                        (const float*)fwd_workspace, (float*)bwd_workspace, (cudaStream_t)stream, 0.f, 0, nullptr, X4, k4, X3, k3,
+                        dX4, dX3);
 }
 
 int renet_dropout_mask(uint64_t seed, uint64_t offset, int64_t n, float p, float* out, void* stream) {

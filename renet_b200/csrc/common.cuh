@@ -74,8 +74,10 @@ int sgemm_tn(const float* A, const int32_t* a_index, int64_t lda, const float* B
 int sgemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
              int64_t M, int32_t N, int32_t K, bool accumulate, cudaStream_t stream);
 
-// 0 = automatic, 1 = tile kernels only, 2 = sliced kernels whenever possible (RENET_GATHER_KERNEL=tile|sliced; rgcn_fwd.cu)
+// 0 = automatic, 1 = tile, 2 = sliced, 3 = stream (RENET_GATHER_KERNEL=tile|sliced|stream; rgcn_fwd.cu)
 int gather_kernel_choice();
+constexpr int64_t kStreamMinEdges = 16384;   // below this a persistent 148-CTA launch costs more than the tile kernel
+bool gather_use_stream(int64_t E);          // the stream kernel (rgcn_stream.cuh) serves this edge count
 
 // tcgen05 GEMM engine building blocks (umma_gemm.cu); gemm_mode() == 1 selects the engine
 int gemm_mode();

@@ -192,7 +192,7 @@ __global__ void fill_rows_kernel(const float* __restrict__ v, float* __restrict_
 struct GruWs {
   float *Brow, *Bent, *Brel, *Bglob, *Whh, *bih, *bhh, *GI, *PQ, *PT, *GH, *Hs;
   float *P_row, *P_ent, *P_rel, *P_glob, *P_hh;   // tensor-core engine: weights packed for umma_gemm_prepacked
-  float *Xd4, *Xd3, *P_x4, *P_x3;                   // input-dropout path: masked inputs [S,4h] / [S,3h], packed W_ih
+  float *Xd4, *Xd3, *P_x4, *P_x3, *zrow;            // input-dropout / dense path: masked inputs [S,4h] / [S,3h], packed W_ih, S zero ints
   float* sync;                                      // grid-barrier counter of the persistent recurrence kernel
   int64_t p_hh_bytes;
   int64_t total_floats;
@@ -224,13 +224,14 @@ GruWs carve(float* base, int64_t S, int64_t Q, int64_t T, int h, int max_len, bo
   w.p_hh_bytes = umma_packed_bytes(3 * h, h);
   w.P_hh = take(2 * w.p_hh_bytes / 4);
   w.sync = take(32);
-  w.Xd4 = w.Xd3 = w.P_x4 = w.P_x3 = nullptr;
+  w.Xd4 = w.Xd3 = w.P_x4 = w.P_x3 = w.zrow = nullptr;
   if (dropout) {
     off = (off + 31) & ~int64_t(31);
     w.P_x4 = take(umma_packed_bytes(3 * h, 4 * h) / 4);
     w.P_x3 = take(umma_packed_bytes(3 * h, 3 * h) / 4);
     w.Xd4 = take(S * 4 * h);
     w.Xd3 = take(S * 3 * h);
+    w.zrow = take(S);
   }
   w.total_floats = off;
   return w;
@@ -272,13 +273,26 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
                    int max_len, const float* w_ih4, const float* w_hh4, const float* b_ih4, const float* b_hh4,
                    const float* w_ih3, const float* w_hh3, const float* b_ih3, const float* b_hh3, float* hn4,
                    float* hn3, int64_t S, int64_t Q, int64_t T, int h, float* ws_base, cudaStream_t stream, float p_drop,
-                   uint64_t seed, const int32_t* row_seq) {
+                   uint64_t seed, const int32_t* row_seq, const float* ext_X4, int k4, const float* ext_X3, int k3) {
+  // ext_X4 != nullptr: "dense" mode -- GRU(s) on caller-materialised inputs X4 [S,k4] (and X3 [S,k3], or nullptr for a single
+  // GRU: the global model's GRU(h,h), global_model.py:25,49); readout / ent / rel / glob / row_glob are not used
+  const bool dense = ext_X4 != nullptr;
+  if (!dense) { k4 = 4 * h; k3 = 3 * h; }
   if (max_len > kMaxLenWs) {
     set_error("renet_gru_fwd: max_len %d exceeds the supported %d", max_len, kMaxLenWs);
     return RENET_ERR_INVALID_ARG;
   }
-  const bool dropout = p_drop > 0.f;
+  const bool dropout = p_drop > 0.f || dense;
   GruWs w = carve(ws_base, S, Q, T, h, kMaxLenWs, dropout);
+  if (dense) {
+    if (k4 <= 0 || k4 > 4 * h || k4 % 4 != 0 || (ext_X3 != nullptr && (k3 <= 0 || k3 > 3 * h || k3 % 4 != 0))) {
+      set_error("renet_gru_dense_fwd: input widths must be multiples of 4 with k4 <= 4h, k3 <= 3h");
+      return RENET_ERR_INVALID_ARG;
+    }
+    RENET_CHECK_CUDA(cudaMemsetAsync(w.zrow, 0, S * sizeof(int32_t), stream));
+    row_glob = reinterpret_cast<const int32_t*>(w.zrow);          // every row reads PT row 0 (= 0)
+    if (ext_X3 == nullptr) { w_ih3 = w_ih4; w_hh3 = w_hh4; b_ih3 = b_ih4; b_hh3 = b_hh4; }   // second encoder: idle copy
+  }
   const dim3 tb(32, 8);
   auto pack = [&](const float* src, int ld_src, int src_off, float* dst, int ld_dst, int dst_off) -> int {
     dim3 grid((3 * h + 31) / 32, (h + 31) / 32);
@@ -295,7 +309,10 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
   if (use_umma) {
     const int t3 = 3 * h / 200;   // column tiles per encoder
     // the packed images only change with the weights: with a declared weight generation they are cached across calls
-    {
+    if (dense) {
+      if ((rc = umma_pack_b(w_hh4, 1, h, 3 * h, h, w.P_hh, 0, stream))) return rc;
+      if ((rc = umma_pack_b(w_hh3, 1, h, 3 * h, h, reinterpret_cast<uint8_t*>(w.P_hh) + w.p_hh_bytes, 0, stream))) return rc;
+    } else {
       const void* keys[5] = {w_ih4, w_ih3, w_hh4, w_hh3, reinterpret_cast<const void*>((intptr_t)h)};
       const int64_t p_bytes = ((w.P_hh - w.P_row) * 4) + 2 * w.p_hh_bytes;
       bool hit = false;
@@ -323,14 +340,23 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
     concat_bias_kernel<<<(6 * h + 255) / 256, 256, 0, stream>>>(b_hh4, b_hh3, w.bhh, 3 * h);
     RENET_CHECK_LAUNCH("concat_bias_kernel");
     if (dropout) {
-      // masked inputs materialised once, projected by two GEMMs: GI = [X4d @ W_ih4^T | X3d @ W_ih3^T]; PQ = b_ih, PT = 0
-      if ((rc = umma_pack_b(w_ih4, 1, 4 * h, 3 * h, 4 * h, w.P_x4, 0, stream))) return rc;
-      if ((rc = umma_pack_b(w_ih3, 1, 3 * h, 3 * h, 3 * h, w.P_x3, 0, stream))) return rc;
-      pack_inputs_dropout_kernel<<<(unsigned)S, 128, 0, stream>>>(H2, readout, row_glob, glob, ent, rel, row_seq, seq_s, seq_r,
-                                                                 w.Xd4, w.Xd3, S, h, p_drop, seed);
-      RENET_CHECK_LAUNCH("pack_inputs_dropout_kernel");
-      if ((rc = umma_gemm_prepacked(w.Xd4, nullptr, 4 * h, w.P_x4, w.GI, 6 * h, nullptr, S, 3 * h, 4 * h, false, 1, 0, 0, 0, stream))) return rc;
-      if ((rc = umma_gemm_prepacked(w.Xd3, nullptr, 3 * h, w.P_x3, w.GI + 3 * h, 6 * h, nullptr, S, 3 * h, 3 * h, false, 1, 0, 0, 0, stream))) return rc;
+      // masked (or caller-provided) inputs materialised once, projected by two GEMMs:
+      // GI = [X4 @ W_ih4^T | X3 @ W_ih3^T]; PQ = b_ih, PT = 0
+      const float* X4 = dense ? ext_X4 : w.Xd4;
+      const float* X3 = dense ? ext_X3 : w.Xd3;
+      if ((rc = umma_pack_b(w_ih4, 1, k4, 3 * h, k4, w.P_x4, 0, stream))) return rc;
+      if (X3 != nullptr && (rc = umma_pack_b(w_ih3, 1, k3, 3 * h, k3, w.P_x3, 0, stream))) return rc;
+      if (!dense) {
+        pack_inputs_dropout_kernel<<<(unsigned)S, 128, 0, stream>>>(H2, readout, row_glob, glob, ent, rel, row_seq, seq_s, seq_r,
+                                                                   w.Xd4, w.Xd3, S, h, p_drop, seed);
+        RENET_CHECK_LAUNCH("pack_inputs_dropout_kernel");
+      }
+      if ((rc = umma_gemm_prepacked(X4, nullptr, k4, w.P_x4, w.GI, 6 * h, nullptr, S, 3 * h, k4, false, 1, 0, 0, 0, stream))) return rc;
+      if (X3 != nullptr) {
+        if ((rc = umma_gemm_prepacked(X3, nullptr, k3, w.P_x3, w.GI + 3 * h, 6 * h, nullptr, S, 3 * h, k3, false, 1, 0, 0, 0, stream))) return rc;
+      } else {
+        RENET_CHECK_CUDA(cudaMemset2DAsync(w.GI + 3 * h, 6 * h * sizeof(float), 0, 3 * h * sizeof(float), S, stream));
+      }
       fill_rows_kernel<<<(unsigned)((Q * 6 * h + 255) / 256), 256, 0, stream>>>(w.bih, w.PQ, Q, 6 * h);
       RENET_CHECK_LAUNCH("fill_rows_kernel");
       RENET_CHECK_CUDA(cudaMemsetAsync(w.PT, 0, T * 6 * h * sizeof(float), stream));
@@ -572,15 +598,22 @@ int launch_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_g
                    float* dw_ih4, float* dw_hh4, float* db_ih4, float* db_hh4, float* dw_ih3, float* dw_hh3,
                    float* db_ih3, float* db_hh3, int64_t N, int64_t S, int64_t Q, int64_t T, int h,
                    const float* fwd_ws, float* bwd_ws, cudaStream_t stream, float p_drop, uint64_t seed,
-                   const int32_t* row_seq) {
-  const bool dropout = p_drop > 0.f;
+                   const int32_t* row_seq, const float* ext_X4, int k4, const float* ext_X3, int k3, float* out_dX4,
+                   float* out_dX3) {
+  const bool dense = ext_X4 != nullptr;
+  if (!dense) { k4 = 4 * h; k3 = 3 * h; }
+  const bool dropout = p_drop > 0.f || dense;
   GruWs f = carve(const_cast<float*>(fwd_ws), S, Q, T, h, kMaxLenWs, dropout);
   GruBwdWs b = carve_bwd(bwd_ws, S, Q, T, h, dropout);
+  if (dense) {
+    row_glob = reinterpret_cast<const int32_t*>(f.zrow);
+    if (ext_X3 == nullptr) { w_ih3 = w_ih4; w_hh3 = w_hh4; }
+  }
   int rc;
   RENET_CHECK_CUDA(cudaMemsetAsync(b.dbias, 0, 12 * h * sizeof(float), stream));
   RENET_CHECK_CUDA(cudaMemsetAsync(b.dWhh, 0, (int64_t)h * 6 * h * sizeof(float), stream));
   RENET_CHECK_CUDA(cudaMemsetAsync(b.dPT, 0, T * 6 * h * sizeof(float), stream));
-  RENET_CHECK_CUDA(cudaMemsetAsync(dH2, 0, N * h * sizeof(float), stream));
+  if (dH2 != nullptr) RENET_CHECK_CUDA(cudaMemsetAsync(dH2, 0, N * h * sizeof(float), stream));
   int last = 0;
   while (last < max_len && host_batch_sizes[last] > 0) ++last;
   if (last > kMaxLenWs) {
@@ -645,13 +678,21 @@ int launch_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_g
   if (dropout) {
     // ---- input-dropout path: dW_ih = dGI^T @ Xd (the masked inputs the forward pass kept), dXd = dGI @ W_ih, then the
     //      masks are regenerated and the gradients scattered to H2 rows / ent / rel / glob -------------------------------------
-    if ((rc = sgemm_tn(b.dGI, nullptr, 6 * h, f.Xd4, 4 * h, dw_ih4, 4 * h, 3 * h, 4 * h, S, true, stream))) return rc;
-    if ((rc = sgemm_tn(b.dGI + 3 * h, nullptr, 6 * h, f.Xd3, 3 * h, dw_ih3, 3 * h, 3 * h, 3 * h, S, true, stream))) return rc;
-    if ((rc = sgemm_nn(b.dGI, nullptr, 6 * h, w_ih4, 4 * h, b.dX4, 4 * h, nullptr, S, 4 * h, 3 * h, false, stream))) return rc;
-    if ((rc = sgemm_nn(b.dGI + 3 * h, nullptr, 6 * h, w_ih3, 3 * h, b.dX3, 3 * h, nullptr, S, 3 * h, 3 * h, false, stream))) return rc;
-    unpack_inputs_dropout_kernel<<<(unsigned)S, 128, 0, stream>>>(b.dX4, b.dX3, readout, row_glob, row_seq, seq_s, seq_r, dH2,
-                                                                 d_ent, d_rel, d_glob, S, h, p_drop, seed);
-    RENET_CHECK_LAUNCH("unpack_inputs_dropout_kernel");
+    const float* X4 = dense ? ext_X4 : f.Xd4;
+    const float* X3 = dense ? ext_X3 : f.Xd3;
+    float* dX4 = dense ? out_dX4 : b.dX4;
+    float* dX3 = dense ? out_dX3 : b.dX3;
+    if ((rc = sgemm_tn(b.dGI, nullptr, 6 * h, X4, k4, dw_ih4, k4, 3 * h, k4, S, true, stream))) return rc;
+    if ((rc = sgemm_nn(b.dGI, nullptr, 6 * h, w_ih4, k4, dX4, k4, nullptr, S, k4, 3 * h, false, stream))) return rc;
+    if (X3 != nullptr) {
+      if ((rc = sgemm_tn(b.dGI + 3 * h, nullptr, 6 * h, X3, k3, dw_ih3, k3, 3 * h, k3, S, true, stream))) return rc;
+      if ((rc = sgemm_nn(b.dGI + 3 * h, nullptr, 6 * h, w_ih3, k3, dX3, k3, nullptr, S, k3, 3 * h, false, stream))) return rc;
+    }
+    if (!dense) {
+      unpack_inputs_dropout_kernel<<<(unsigned)S, 128, 0, stream>>>(b.dX4, b.dX3, readout, row_glob, row_seq, seq_s, seq_r, dH2,
+                                                                   d_ent, d_rel, d_glob, S, h, p_drop, seed);
+      RENET_CHECK_LAUNCH("unpack_inputs_dropout_kernel");
+    }
     const dim3 tbd(32, 8);
     auto unpack_hh = [&](const float* src, int src_off, float* dst) -> int {
       dim3 grid((3 * h + 31) / 32, (h + 31) / 32);
@@ -660,9 +701,10 @@ int launch_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_g
       return RENET_OK;
     };
     if ((rc = unpack_hh(b.dWhh, 0, dw_hh4))) return rc;
-    if ((rc = unpack_hh(b.dWhh, 3 * h, dw_hh3))) return rc;
+    if (dw_hh3 != nullptr && (rc = unpack_hh(b.dWhh, 3 * h, dw_hh3))) return rc;
     float* outs[4] = {db_ih4, db_ih3, db_hh4, db_hh3};
     for (int k = 0; k < 4; ++k) {
+      if (outs[k] == nullptr) continue;                     // single GRU: the idle second encoder has no gradients
       dim3 grid((3 * h + 127) / 128, 1);
       colsum_accum_kernel<<<grid, 128, 0, stream>>>(b.dbias + (int64_t)k * 3 * h, 3 * h, 1, 3 * h, outs[k], 1);
       RENET_CHECK_LAUNCH("colsum_accum_kernel");

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "rgcn_tile.cuh"
 #include "rgcn_sliced.cuh"
+#include "rgcn_stream.cuh"
 
 namespace renet {
 namespace {
@@ -298,6 +299,23 @@ int launch_rgcn_bwd(const float* H, const int32_t* h_index, const float* W, cons
         rgcn_gather_sliced_kernel<false, false, false, true><<<kNumSMs, kSlThreads, smem, stream>>>(
             P, nullptr, w_map, t_row_ptr, t_col_dst, t_col_type, norm, dH, (int)N, R2);
       RENET_CHECK_LAUNCH("rgcn_gather_sliced_kernel(bwd)");
+    } else if (E > 0 && gather_use_stream(E)) {
+      // batch scale: the persistent bulk-copy kernel on the reversed graph -- no atomics, bitwise reproducible dH
+      static bool attr_done = false;
+      if (!attr_done) {
+        RENET_CHECK_CUDA(cudaFuncSetAttribute(rgcn_gather_stream_kernel<false, true, false, true>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStSmemBytes));
+        RENET_CHECK_CUDA(cudaFuncSetAttribute(rgcn_gather_stream_kernel<false, false, false, true>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStSmemBytes));
+        attr_done = true;
+      }
+      if (Wloop != nullptr)
+        rgcn_gather_stream_kernel<false, true, false, true><<<kNumSMs, kStThreads, kStSmemBytes, stream>>>(
+            P, nullptr, W, t_row_ptr, t_col_dst, t_col_type, norm, dH, (int)N);
+      else
+        rgcn_gather_stream_kernel<false, false, false, true><<<kNumSMs, kStThreads, kStSmemBytes, stream>>>(
+            P, nullptr, W, t_row_ptr, t_col_dst, t_col_type, norm, dH, (int)N);
+      RENET_CHECK_LAUNCH("rgcn_gather_stream_kernel(bwd)");
     } else {
       const unsigned grid = (unsigned)((N + kTileNodes - 1) / kTileNodes);
       if (Wloop != nullptr)

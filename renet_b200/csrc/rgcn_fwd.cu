@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "rgcn_tile.cuh"
 #include "rgcn_sliced.cuh"
+#include "rgcn_stream.cuh"
 
 namespace renet {
 namespace {
@@ -100,18 +101,39 @@ __global__ void rgcn_gather_generic_kernel(const float* __restrict__ H, const in
 
 }  // namespace
 
-// Which kernel serves the d=200 shape: 0 = default (the tile kernel), 1 = tile, 2 = the sliced kernel whenever its shared
-// memory allows.  RENET_GATHER_KERNEL=tile|sliced picks one per process for A/B measurements (tools/bench_gather.py); results
-// agree to fp32 summation order.  Measured on B200 at ICEWS18 scale: tile 49 us, sliced 82-98 us -- the
-// sliced kernel moves 20 % fewer bytes through L2 but at 16 warps/SM and ~40 instructions per 3 edge-slices it is issue-bound,
-// so it stays opt-in.
+// Which kernel serves the d=200 shape: 0 = automatic (the stream kernel at batch scale, the tile kernel for small graphs),
+// 1 = tile, 2 = sliced (whenever its shared memory allows), 3 = stream.  RENET_GATHER_KERNEL=tile|sliced|stream picks one per
+// process for A/B measurements (tools/bench_gather.py); results agree to fp32 summation order.
 int gather_kernel_choice() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("RENET_GATHER_KERNEL");
-    v = (e && e[0] == 't') ? 1 : ((e && e[0] == 's') ? 2 : 0);
+    v = 0;
+    if (e && e[0] == 't') v = 1;
+    else if (e && e[0] == 's' && e[1] == 'l') v = 2;
+    else if (e && e[0] == 's') v = 3;
   }
   return v;
+}
+bool gather_use_stream(int64_t E) {
+  const int c = gather_kernel_choice();
+  return c == 3 || (c == 0 && E >= kStreamMinEdges);
+}
+
+template <bool RELU, bool HAS_LOOP, bool INDEXED>
+static int launch_stream(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
+                         const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout, int N,
+                         cudaStream_t stream) {
+  static bool attr_done = false;        // one device per process (one process per GPU)
+  if (!attr_done) {
+    RENET_CHECK_CUDA(cudaFuncSetAttribute(rgcn_gather_stream_kernel<RELU, HAS_LOOP, INDEXED, false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStSmemBytes));
+    attr_done = true;
+  }
+  rgcn_gather_stream_kernel<RELU, HAS_LOOP, INDEXED, false><<<kNumSMs, kStThreads, kStSmemBytes, stream>>>(
+      H, h_index, W, row_ptr, col_src, col_type, norm, Hout, N);
+  RENET_CHECK_LAUNCH("rgcn_gather_stream_kernel");
+  return RENET_OK;
 }
 
 template <bool RELU, bool HAS_LOOP, bool INDEXED>
@@ -161,6 +183,20 @@ int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, c
         default: RENET_LAUNCH_SLICED(true, true, true);
       }
 #undef RENET_LAUNCH_SLICED
+    }
+    if (!passthrough && gather_use_stream(E)) {
+#define RENET_LAUNCH_STREAM(R, L, I) return launch_stream<R, L, I>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, stream)
+      switch (key) {
+        case 0: RENET_LAUNCH_STREAM(false, false, false);
+        case 1: RENET_LAUNCH_STREAM(false, false, true);
+        case 2: RENET_LAUNCH_STREAM(false, true, false);
+        case 3: RENET_LAUNCH_STREAM(false, true, true);
+        case 4: RENET_LAUNCH_STREAM(true, false, false);
+        case 5: RENET_LAUNCH_STREAM(true, false, true);
+        case 6: RENET_LAUNCH_STREAM(true, true, false);
+        default: RENET_LAUNCH_STREAM(true, true, true);
+      }
+#undef RENET_LAUNCH_STREAM
     }
     const unsigned block = kTileWarps * 32;
     const unsigned n_tiles = (unsigned)((N + kTileNodes - 1) / kTileNodes);

@@ -107,3 +107,18 @@ def check_eval_against_golden(res, ev, tol=1e-4):
     # ranks are integers / half-integers: exact
     assert np.array_equal(res['raw'], ev['raw'])
     assert np.array_equal(res['filt'], ev['filt'])
+
+
+def global_setup():
+    """Inputs of tests/golden/global_tiny.npz (written by oracle/gen_golden.gen_global_tiny from the unmodified reference):
+    the tiny stream's quadruples, deterministic RENet_global parameters, the batch of timestamps and soft targets."""
+    from oracle.gen_golden import det_params
+    g = load_npz('global_tiny.npz')
+    tiny = load_npz('renet_tiny.npz')
+    quads = tiny['quads'].astype(np.int64)
+    shapes = {str(k): tuple(int(x) for x in v[:2] if x > 0) for k, v in zip(g['shapes_keys'], g['shapes_vals'])}
+    params = det_params(shapes, int(g['seed']))
+    sel = [int(i) for i in g['t_batch']]
+    return dict(g=g, quads=quads, num_e=int(tiny['num_e']), R=int(tiny['R']), h=int(g['h']), params=params, sel=sel,
+                times=g['times'].astype(np.int64), t_batch=g['times'].astype(np.int64)[sel],
+                tps=g['true_prob_s'], tpo=g['true_prob_o'])

@@ -183,11 +183,13 @@ def test_full_size_properties(G):
     assert torch.equal(G.layer_fwd(H, None, W, Wl, rp, cs, ct, norm, N, E, 200, 200, 100, False), a)
 
 
-@pytest.mark.parametrize('N,E,heavy,empty_frac', [(5000, 40000, 6000, 0.25), (120, 20000, 0, 0.0), (40000, 17000, 0, 0.7)])
-def test_sliced_kernel_edge_cases_fwd_bwd_vs_oracle(G, N, E, heavy, empty_frac):
-    """The feature-sliced persistent kernel (rgcn_sliced.cuh; taken for E >= 16384) on graphs that stress its hand-over
-    logic: destinations without in-edges (also leading / trailing ones), a destination heavier than a whole warp's share
-    (cut by group boundaries twice), far fewer destinations than warps, far more destinations than edges.  Forward and
+@pytest.mark.parametrize('N,E,heavy,empty_frac', [(5000, 40000, 6000, 0.25), (120, 20000, 0, 0.0), (40000, 17000, 0, 0.7),
+                                                  (700000, 17000, 0, 0.9)])
+def test_batch_scale_kernel_edge_cases_fwd_bwd_vs_oracle(G, N, E, heavy, empty_frac):
+    """The persistent batch-scale kernel (rgcn_stream.cuh; taken for E >= 16384) on graphs that stress its partition and
+    hand-over logic: destinations without in-edges (also leading / trailing ones), a destination heavier than a whole
+    CTA's share (its edges span all warps of one CTA: a chain of heads), far fewer destinations than warps, far more
+    destinations than edges, and more destinations per CTA than the shared-memory row_ptr slice holds.  Forward and
     backward (dH through the same kernel on the reversed graph) against the CPU oracle; bitwise reproducible."""
     rng = np.random.RandomState(N + E)
     R2 = 480

@@ -1,7 +1,7 @@
 """Micro-benchmark + cross-check of the fused gather kernels on dataset-shaped batches (run on the GPU box).
 
     RENET_GATHER_KERNEL=tile   python tools/bench_gather.py [icews18|gdelt|icews14] [timestamps]
-    RENET_GATHER_KERNEL=sliced python tools/bench_gather.py ...
+    RENET_GATHER_KERNEL=stream python tools/bench_gather.py ...        (or sliced)
 
 The kernel choice is read once per process (environment), so an A/B is two runs; each run also writes a checksum of the
 layer outputs so the two kernels can be compared (they agree to fp32 summation order, not bit for bit)."""
@@ -73,9 +73,9 @@ for layer1 in (True, False):
     call(hb, g, H, out, layer1)
     print('  reproducible bit for bit:', bool(torch.equal(first, out)), ' checksum %.6f' % float(out.double().sum()))
 os.makedirs('gpurun_out', exist_ok=True)
-path = 'gpurun_out/gather_%s_%s.npz' % (preset, kernel)
+path = '/tmp/gather_%s_%s.npz' % (preset, kernel)
 np.savez(path, **res)
-other = 'gpurun_out/gather_%s_%s.npz' % (preset, 'tile' if kernel != 'tile' else 'sliced')
+other = '/tmp/gather_%s_%s.npz' % (preset, 'tile' if kernel != 'tile' else 'stream')
 if os.path.exists(other):
     o = np.load(other)
     for k in res:
