@@ -424,6 +424,7 @@ def run_ours(args):
                       agg.rgcn2.loop_weight.detach())
     P = _lib.ptr
     stream = _lib.stream()
+    hot_rel = gstore.hot_relations(dev)
 
     def layer(d, H, h_index, W, Wl, out, relu, ev=None, sub=None):
         g = d['g']
@@ -436,8 +437,9 @@ def run_ours(args):
         _lib.check(L.renet_selfloop_gemm(P(H), P(loop_index), P(Wl), P(out), rows, H_DIM, H_DIM, stream), 'gemm')
         if ev is not None:
             ev[0].record()
-        _lib.check(L.renet_rgcn_gather(P(H), P(h_index), P(W), P(rp), P(cs), P(ct), P(nm),
-                                       P(out), rows, n_e, H_DIM, H_DIM, NUM_BASES, R2, int(relu), 1, stream), 'gather')
+        hot = hot_rel[d['reverse']]     # the dataset's relation ranking (GraphStore.hot_relations): part of the graph store
+        _lib.check(L.renet_rgcn_gather_hot(P(H), P(h_index), P(W), P(rp), P(cs), P(ct), P(nm), P(out), rows, n_e, H_DIM, H_DIM,
+                                           NUM_BASES, R2, int(relu), 1, P(hot), hot.numel(), stream), 'gather')
         if ev is not None:
             ev[1].record()
 
@@ -508,7 +510,7 @@ def run_ours(args):
                 g2_bytes.append(algorithmic_bytes(d['sub'].sizes()[0], d['sub'].E, R2))
     peak, peak_src = measured_peak_gbs()
     achieved = float(np.sum(g_bytes) / (np.sum(g_ms) * 1e-3) / 1e9)
-    roofline = {'kernel': 'rgcn_gather_d200_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+    roofline = {'kernel': 'rgcn_gather_stream_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': ncu_traffic(), 'peak_source': peak_src,
                 'avg_launch_us': float(np.mean(g_ms) * 1e3), 'algorithmic_bytes_per_launch': float(np.mean(g_bytes)),
                 'launches': 'layer-1 launches (whole batched graph); layer 2 runs the same kernel on the read-out sub-graph: '
@@ -523,6 +525,26 @@ def run_ours(args):
                      'tensor_tflops_3xtf32': float(3 * np.sum(mm_flops) / (np.sum(mm_ms) * 1e-3) / 1e12), 'tf32_peak_tflops': tf32_peak,
                      'note': 'N x 200 x 200 per launch: the memory floor (rows in + rows out) and the 3xTF32 tensor floor are within '
                              '20 % of each other; timed with the packing launch of a new weight generation included'}
+
+    if os.environ.get('RENET_STREAM_TL') == '1' and rank == 0:
+        # debug: per-warp time stamps of ONE layer-1 gather launch in the middle of a step (tools/stream_timeline.py explains them)
+        WARPS = int(os.environ.get('RENET_STREAM_WARPS', '32'))
+        buf = torch.zeros(148 * WARPS * 8, dtype=torch.int64, device=dev)
+        e = pool[(args.warmup + 3) % len(pool)]
+        d = e['dirs'][0]
+        _lib.check(L.renet_selfloop_gemm(P(ent), P(d['g'].node_ent), P(L1), P(d['H1']), d['g'].N, H_DIM, H_DIM, stream), 'gemm')
+        L.renet_debug_stream_timing(P(buf))
+        hot = hot_rel[False]
+        _lib.check(L.renet_rgcn_gather_hot(P(ent), P(d['g'].node_ent), P(W1), P(d['g'].row_ptr), P(d['g'].col_src), P(d['ct']), P(d['g'].norm),
+                                           P(d['H1']), d['g'].N, d['g'].E, H_DIM, H_DIM, NUM_BASES, R2, 1, 1, P(hot), hot.numel(), stream), 'gather')
+        torch.cuda.synchronize()
+        L.renet_debug_stream_timing(None)
+        t = buf.cpu().numpy().reshape(148, WARPS, 8).astype(np.float64)
+        g0 = t[:, :, 5].min()
+        ph = [(t[:, :, 1] - t[:, :, 0]) / 1965.0, (t[:, :, 2] - t[:, :, 1]) / 1965.0, (t[:, :, 3] - t[:, :, 2]) / 1965.0, (t[:, :, 4] - t[:, :, 3]) / 1965.0]
+        sys.stderr.write('stream timeline in context: span %.1f us, entry skew %.1f us; medians (us): search %.1f, prologue %.1f, loop %.1f, tail %.1f; '
+                         'max loop %.1f\n' % ((t[:, :, 6].max() - g0) / 1e3, (t[:, :, 5].min(1).max() - g0) / 1e3, np.median(ph[0]), np.median(ph[1]),
+                                              np.median(ph[2]), np.median(ph[3]), ph[2].max()))
 
     # ---- GRU (reported separately) -------------------------------------------------------------------------
     from renet_b200.gru import fused_gru

@@ -113,6 +113,21 @@ int renet_rgcn_gather(const float* H, const int32_t* h_index, const float* W,
                       const float* norm, float* Hout,
                       int64_t N, int64_t E, int32_t d_in, int32_t d_out,
                       int32_t num_bases, int32_t R2, int32_t relu, int32_t has_loop, void* stream);
+/* Same, with the caller's list of the most frequent relation ids (device int32 [n_hot], every id < R2, most frequent
+ * first): at batch scale the kernel keeps the block table rows of the first few dozen of them in shared memory instead of
+ * fetching a 1600-byte row per edge.  Relation frequencies are a property of the dataset (count edata['type_s'] /
+ * ['type_o'] over graph_dict once); without a list (n_hot = 0, or renet_rgcn_gather) every CTA ranks the relations of its
+ * own edges in its prologue.  The list only changes where a row is read from: results are bit-identical. */
+int renet_rgcn_gather_hot(const float* H, const int32_t* h_index, const float* W,
+                          const int32_t* row_ptr, const int32_t* col_src, const int32_t* col_type,
+                          const float* norm, float* Hout,
+                          int64_t N, int64_t E, int32_t d_in, int32_t d_out,
+                          int32_t num_bases, int32_t R2, int32_t relu, int32_t has_loop,
+                          const int32_t* hot_rel, int32_t n_hot, void* stream);
+/* DEBUG ONLY (tools/stream_timeline.py): while `buffer` (device, 148 x 16 x 8 int64) is non-NULL, every batch-scale forward
+ * gather launch writes per-warp time stamps into it (SM clock at entry / after the partition / first edge / last edge /
+ * exit, global timer at entry and exit, edge count).  Pass NULL to switch it off; never set in production code. */
+int renet_debug_stream_timing(void* buffer);
 
 /* ------------------------------------------------------------------------------------------------
  * RGCN block-diagonal layer, backward (autograd of the above; the reference relies on
@@ -387,7 +402,8 @@ int renet_prepare_sequences(const int64_t* triplets, int32_t ld, int32_t col_s, 
  *   hn4, hn3 = renet_gru_fwd(H2, ...)                          (Aggregator.py:139-165 + model.py:86,94)
  * Same arguments as the individual entry points; H1/H2 [N,h] are caller-provided outputs.  With a read-out sub-graph
  * (sub_* = the outputs of renet_readout_subgraph for this batch and type column; all NULL = none) layer 2 runs on it:
- * H2 then holds S compact rows and the GRU reads them through sub_readout. */
+ * H2 then holds S compact rows and the GRU reads them through sub_readout.  hot_rel / n_hot: the optional relation ranking
+ * of renet_rgcn_gather_hot (NULL / 0 = none), used by both layers. */
 int renet_encode_fwd(const float* ent, const int32_t* node_ent, const int32_t* row_ptr, const int32_t* col_src,
                      const int32_t* col_type, const float* norm,
                      const float* W1, const float* Wloop1, const float* W2, const float* Wloop2,
@@ -400,6 +416,7 @@ int renet_encode_fwd(const float* ent, const int32_t* node_ent, const int32_t* r
                      float* hn4, float* hn3, int64_t S, int64_t Q, int64_t T, int32_t h, int32_t num_bases,
                      const int32_t* sub_uniq, const int32_t* sub_readout, const int32_t* sub_row_ptr,
                      const int32_t* sub_col_src, const int32_t* sub_col_type, const float* sub_norm,
+                     const int32_t* hot_rel, int32_t n_hot,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Materialise the packed GRU inputs exactly as the reference's aggregator returns them

@@ -28,6 +28,8 @@ SIGNATURES = {
     'renet_selfloop_gemm': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     'renet_selfloop_gemm_bwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     'renet_rgcn_gather': (ctypes.c_int, [_vp] * 8 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    'renet_debug_stream_timing': (ctypes.c_int, [_vp]),
+    'renet_rgcn_gather_hot': (ctypes.c_int, [_vp] * 8 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     'renet_rgcn_block_bwd': (ctypes.c_int, [_vp] * 17 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     'renet_rgcn_bipartite_bwd': (ctypes.c_int, [_vp] * 14 + [_i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     'renet_readout_subgraph_workspace_bytes': (_i64, [_i64, _i64]),
@@ -52,7 +54,7 @@ SIGNATURES = {
     'renet_induce_workspace_bytes': (_i64, [_i64]),
     'renet_induce_edges': (ctypes.c_int, [_vp] * 9 + [_i64, _i64, _i64] + [_vp] * 7 + [_i64, _vp]),
     'renet_encode_fwd': (ctypes.c_int, [_vp] * 12 + [_i64, _i64, _i32] + [_vp] * 9 + [_i32] + [_vp] * 10 +
-                         [_i64, _i64, _i64, _i32, _i32] + [_vp] * 6 + [_vp, _i64, _vp]),
+                         [_i64, _i64, _i64, _i32, _i32] + [_vp] * 6 + [_vp, _i32] + [_vp, _i64, _vp]),
     'renet_loader_create': (_vp, [_i32]),
     'renet_loader_destroy': (None, [_vp]),
     'renet_loader_submit_plan': (_i64, [_vp, _i64] + [_vp] * 10 + [_i64, _i32, _vp, _vp, _i64, _vp, _i32, _vp]),

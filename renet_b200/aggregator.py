@@ -202,6 +202,7 @@ class RGCNAggregator(nn.Module):
         ws = torch.empty(nbytes // 4 + 4, dtype=torch.float32, device=dev)
         bs = hb.batch_sizes
         l1, l2 = self.rgcn1, self.rgcn2
+        hot = g.hot_rel(reverse)
         rc = L.renet_encode_fwd(P(ent_embeds), P(g.node_ent), P(g.row_ptr), P(g.col_src), P(g.col_type(reverse)),
                                 P(g.norm), P(l1.weight), P(l1.loop_weight), P(l2.weight), P(l2.loop_weight), P(H),
                                 P(H[g.N:]), g.N, g.E_launch, l1.weight.shape[0], P(hb.readout), P(row_glob), P(glob), P(rel),
@@ -209,6 +210,6 @@ class RGCNAggregator(nn.Module):
                                 bs.ctypes.data_as(_lib.ctypes.c_void_p), len(bs), P(p4[0]), P(p4[1]), P(p4[2]), P(p4[3]),
                                 P(p3[0]), P(p3[1]), P(p3[2]), P(p3[3]), P(hn[0]), P(hn[1]), hb.S, Q, T, h, l1.num_bases,
                                 P(sub.uniq), P(sub.readout_c), P(sub.row_ptr), P(sub.col_src), P(sub.col_type(reverse)),
-                                P(sub.norm), P(ws), nbytes, _lib.stream())
+                                P(sub.norm), P(hot), 0 if hot is None else hot.numel(), P(ws), nbytes, _lib.stream())
         _lib.check(rc, 'renet_encode_fwd')
         return hn[0], hn[1], hb

@@ -23,7 +23,7 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
                        const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout,
                        int64_t N, int64_t E, int d_in, int d_out, int nb, int relu, int has_loop,
-                       cudaStream_t stream, int R2 = -1);
+                       cudaStream_t stream, int R2 = -1, const int32_t* hot_rel = nullptr, int n_hot = 0);
 int launch_rgcn_bwd(const float* H, const int32_t* h_index, const float* W, const float* Wloop,
                     const int32_t* t_row_ptr, const int32_t* t_col_dst, const int32_t* t_col_type,
                     const int32_t* rel_ptr, const int32_t* rel_src, const int32_t* rel_dst, const float* norm,
@@ -200,6 +200,23 @@ int renet_rgcn_gather(const float* H, const int32_t* h_index, const float* W, co
   RENET_CHECK_ARG(E == 0 || (col_src && col_type), "renet_rgcn_gather: null edge arrays");
   return launch_rgcn_gather(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, N, E, d_in, d_out, num_bases,
                             relu, has_loop, (cudaStream_t)stream, R2);
+}
+
+int renet_rgcn_gather_hot(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
+                          const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout, int64_t N,
+                          int64_t E, int32_t d_in, int32_t d_out, int32_t num_bases, int32_t R2, int32_t relu,
+                          int32_t has_loop, const int32_t* hot_rel, int32_t n_hot, void* stream) {
+  int rc = check_layer_args("renet_rgcn_gather_hot", H, W, row_ptr, norm, Hout, N, E, d_in, d_out, num_bases, R2);
+  if (rc) return rc;
+  RENET_CHECK_ARG(E == 0 || (col_src && col_type), "renet_rgcn_gather_hot: null edge arrays");
+  RENET_CHECK_ARG(n_hot >= 0 && (n_hot == 0 || hot_rel != nullptr), "renet_rgcn_gather_hot: bad hot-relation list");
+  return launch_rgcn_gather(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, N, E, d_in, d_out, num_bases,
+                            relu, has_loop, (cudaStream_t)stream, R2, n_hot > 0 ? hot_rel : nullptr, n_hot);
+}
+
+int renet_debug_stream_timing(void* buffer) {
+  set_stream_debug_buffer(static_cast<long long*>(buffer));
+  return RENET_OK;
 }
 
 int renet_rgcn_block_fwd(const float* H, const int32_t* h_index, const float* W, const float* Wloop,
@@ -429,12 +446,23 @@ int renet_encode_fwd(const float* ent, const int32_t* node_ent, const int32_t* r
                      const float* b_ih4, const float* b_hh4, const float* w_ih3, const float* w_hh3, const float* b_ih3,
                      const float* b_hh3, float* hn4, float* hn3, int64_t S, int64_t Q, int64_t T, int32_t h,
                      int32_t num_bases, const int32_t* sub_uniq, const int32_t* sub_readout, const int32_t* sub_row_ptr,
-                     const int32_t* sub_col_src, const int32_t* sub_col_type, const float* sub_norm, void* workspace,
-                     int64_t workspace_bytes, void* stream) {
+                     const int32_t* sub_col_src, const int32_t* sub_col_type, const float* sub_norm, const int32_t* hot_rel,
+                     int32_t n_hot, void* workspace, int64_t workspace_bytes, void* stream) {
+  RENET_CHECK_ARG(n_hot >= 0 && (n_hot == 0 || hot_rel != nullptr), "renet_encode_fwd: bad hot-relation list");
+  if (n_hot == 0) hot_rel = nullptr;
   // layer 1 (embedding lookup fused through node_ent, ReLU), layer 2 (linear), then read-out + both GRUs
-  int rc = renet_rgcn_block_fwd(ent, node_ent, W1, Wloop1, row_ptr, col_src, col_type, norm, H1, N, E, h, h, num_bases, R2,
-                                1, stream);
+  int rc = check_layer_args("renet_encode_fwd", ent, W1, row_ptr, norm, H1, N, E, h, h, num_bases, R2);
   if (rc) return rc;
+  RENET_CHECK_ARG(E == 0 || (col_src && col_type), "renet_encode_fwd: null edge arrays");
+  if (N > 0) {
+    if (Wloop1 != nullptr) {
+      rc = sgemm_nn(ent, node_ent, h, Wloop1, h, H1, h, nullptr, N, h, h, false, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+    rc = launch_rgcn_gather(ent, node_ent, W1, row_ptr, col_src, col_type, norm, H1, N, E, h, h, num_bases, 1,
+                            Wloop1 != nullptr, (cudaStream_t)stream, R2, hot_rel, n_hot);
+    if (rc) return rc;
+  }
   if (sub_uniq != nullptr) {
     // layer 2 on the read-out sub-graph (renet_readout_subgraph): S compact destinations, sources = rows of H1
     RENET_CHECK_ARG(sub_readout && sub_row_ptr && sub_col_src && sub_col_type && sub_norm,
@@ -445,7 +473,7 @@ int renet_encode_fwd(const float* ent, const int32_t* node_ent, const int32_t* r
         if (rc) return rc;
       }
       rc = launch_rgcn_gather(H1, nullptr, W2, sub_row_ptr, sub_col_src, sub_col_type, sub_norm, H2, S, E > 0 ? E : 1, h, h,
-                              num_bases, 0, Wloop2 != nullptr, (cudaStream_t)stream, R2);
+                              num_bases, 0, Wloop2 != nullptr, (cudaStream_t)stream, R2, hot_rel, n_hot);
       if (rc) return rc;
     }
     readout = sub_readout;

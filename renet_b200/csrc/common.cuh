@@ -77,7 +77,9 @@ int sgemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
 // 0 = automatic, 1 = tile, 2 = sliced, 3 = stream (RENET_GATHER_KERNEL=tile|sliced|stream; rgcn_fwd.cu)
 int gather_kernel_choice();
 constexpr int64_t kStreamMinEdges = 16384;   // below this a persistent 148-CTA launch costs more than the tile kernel
-bool gather_use_stream(int64_t E);          // the stream kernel (rgcn_stream.cuh) serves this edge count
+constexpr int64_t kStreamMinNodes = 16384;
+bool gather_use_stream(int64_t E, int64_t N);
+void set_stream_debug_buffer(long long* p);   // debug: per-warp time stamps of the stream kernel (rgcn_fwd.cu)          // the stream kernel (rgcn_stream.cuh) serves this edge count
 
 // tcgen05 GEMM engine building blocks (umma_gemm.cu); gemm_mode() == 1 selects the engine
 int gemm_mode();

@@ -299,22 +299,22 @@ int launch_rgcn_bwd(const float* H, const int32_t* h_index, const float* W, cons
         rgcn_gather_sliced_kernel<false, false, false, true><<<kNumSMs, kSlThreads, smem, stream>>>(
             P, nullptr, w_map, t_row_ptr, t_col_dst, t_col_type, norm, dH, (int)N, R2);
       RENET_CHECK_LAUNCH("rgcn_gather_sliced_kernel(bwd)");
-    } else if (E > 0 && gather_use_stream(E)) {
+    } else if (E > 0 && gather_use_stream(E, N)) {
       // batch scale: the persistent bulk-copy kernel on the reversed graph -- no atomics, bitwise reproducible dH
       static bool attr_done = false;
       if (!attr_done) {
         RENET_CHECK_CUDA(cudaFuncSetAttribute(rgcn_gather_stream_kernel<false, true, false, true>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStSmemBytes));
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, StDefault<true>::kSmemBytes));
         RENET_CHECK_CUDA(cudaFuncSetAttribute(rgcn_gather_stream_kernel<false, false, false, true>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStSmemBytes));
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, StDefault<true>::kSmemBytes));
         attr_done = true;
       }
       if (Wloop != nullptr)
-        rgcn_gather_stream_kernel<false, true, false, true><<<kNumSMs, kStThreads, kStSmemBytes, stream>>>(
-            P, nullptr, W, t_row_ptr, t_col_dst, t_col_type, norm, dH, (int)N);
+        rgcn_gather_stream_kernel<false, true, false, true><<<kNumSMs, StDefault<true>::kThreads, StDefault<true>::kSmemBytes, stream>>>(
+            P, nullptr, W, t_row_ptr, t_col_dst, t_col_type, norm, dH, (int)N, R2, nullptr, 0, (int)E, nullptr);
       else
-        rgcn_gather_stream_kernel<false, false, false, true><<<kNumSMs, kStThreads, kStSmemBytes, stream>>>(
-            P, nullptr, W, t_row_ptr, t_col_dst, t_col_type, norm, dH, (int)N);
+        rgcn_gather_stream_kernel<false, false, false, true><<<kNumSMs, StDefault<true>::kThreads, StDefault<true>::kSmemBytes, stream>>>(
+            P, nullptr, W, t_row_ptr, t_col_dst, t_col_type, norm, dH, (int)N, R2, nullptr, 0, (int)E, nullptr);
       RENET_CHECK_LAUNCH("rgcn_gather_stream_kernel(bwd)");
     } else {
       const unsigned grid = (unsigned)((N + kTileNodes - 1) / kTileNodes);

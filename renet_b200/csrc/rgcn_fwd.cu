@@ -115,25 +115,58 @@ int gather_kernel_choice() {
   }
   return v;
 }
-bool gather_use_stream(int64_t E) {
+bool gather_use_stream(int64_t E, int64_t N) {
+  // E may be an upper bound (device-assembled batches and read-out sub-graphs pass their capacity), so the destination
+  // count decides with it: the persistent kernel pays ~5 us of prologue per launch, which a few thousand destinations'
+  // worth of edges does not amortise (read-out sub-graph of an ICEWS18 batch: tile kernel 26 us, stream kernel 43 us)
   const int c = gather_kernel_choice();
-  return c == 3 || (c == 0 && E >= kStreamMinEdges);
+  return c == 3 || (c == 0 && E >= kStreamMinEdges && N >= kStreamMinNodes);
+}
+
+// debug hook (tools/stream_timeline.py): per-warp time stamps of the next stream-kernel launches; never set in production
+static long long* g_stream_dbg = nullptr;
+void set_stream_debug_buffer(long long* p) { g_stream_dbg = p; }
+
+int stream_cfg_choice() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RENET_STREAM_CFG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+template <bool RELU, bool HAS_LOOP, bool INDEXED, class Cfg>
+static int launch_stream_cfg(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
+                             const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout, int N, int R2,
+                             const int32_t* hot_rel, int n_hot, int E_hint, cudaStream_t stream) {
+  static bool attr_done = false;        // one device per process (one process per GPU)
+  if (!attr_done) {
+    RENET_CHECK_CUDA(cudaFuncSetAttribute(rgcn_gather_stream_kernel<RELU, HAS_LOOP, INDEXED, false, Cfg>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  rgcn_gather_stream_kernel<RELU, HAS_LOOP, INDEXED, false, Cfg><<<kNumSMs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
+      H, h_index, W, row_ptr, col_src, col_type, norm, Hout, N, R2, hot_rel, n_hot, E_hint, g_stream_dbg);
+  RENET_CHECK_LAUNCH("rgcn_gather_stream_kernel");
+  return RENET_OK;
 }
 
 template <bool RELU, bool HAS_LOOP, bool INDEXED>
 static int launch_stream(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
-                         const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout, int N,
-                         cudaStream_t stream) {
-  static bool attr_done = false;        // one device per process (one process per GPU)
-  if (!attr_done) {
-    RENET_CHECK_CUDA(cudaFuncSetAttribute(rgcn_gather_stream_kernel<RELU, HAS_LOOP, INDEXED, false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStSmemBytes));
-    attr_done = true;
+                         const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout, int N, int R2,
+                         const int32_t* hot_rel, int n_hot, int E_hint, cudaStream_t stream) {
+#define RENET_ST(...) return launch_stream_cfg<RELU, HAS_LOOP, INDEXED, __VA_ARGS__>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, N, R2, hot_rel, n_hot, E_hint, stream)
+  if (RELU && HAS_LOOP) {               // experiment configurations exist for the layer-1 shape only (RENET_STREAM_CFG)
+    switch (stream_cfg_choice()) {
+      case 1: RENET_ST(StCfg<24, 2, 44, false>);
+      case 2: RENET_ST(StCfg<28, 2, 31, false>);
+      case 3: RENET_ST(StCfg<16, 4, 31, false>);
+      default: break;
+    }
   }
-  rgcn_gather_stream_kernel<RELU, HAS_LOOP, INDEXED, false><<<kNumSMs, kStThreads, kStSmemBytes, stream>>>(
-      H, h_index, W, row_ptr, col_src, col_type, norm, Hout, N);
-  RENET_CHECK_LAUNCH("rgcn_gather_stream_kernel");
-  return RENET_OK;
+  RENET_ST(StDefault<false>);
+#undef RENET_ST
 }
 
 template <bool RELU, bool HAS_LOOP, bool INDEXED>
@@ -159,7 +192,7 @@ static int launch_sliced(const float* H, const int32_t* h_index, const float* W,
 int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
                        const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout,
                        int64_t N, int64_t E, int d_in, int d_out, int nb, int relu, int has_loop,
-                       cudaStream_t stream, int R2) {
+                       cudaStream_t stream, int R2, const int32_t* hot_rel, int n_hot) {
   if (N == 0) return RENET_OK;
   const int passthrough = (E == 0) ? 1 : 0;
   const bool fast = d_in == 200 && d_out == 200 && nb == 100 &&
@@ -184,8 +217,8 @@ int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, c
       }
 #undef RENET_LAUNCH_SLICED
     }
-    if (!passthrough && gather_use_stream(E)) {
-#define RENET_LAUNCH_STREAM(R, L, I) return launch_stream<R, L, I>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, stream)
+    if (!passthrough && gather_use_stream(E, N)) {
+#define RENET_LAUNCH_STREAM(R, L, I) return launch_stream<R, L, I>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, R2, hot_rel, n_hot, (int)E, stream)
       switch (key) {
         case 0: RENET_LAUNCH_STREAM(false, false, false);
         case 1: RENET_LAUNCH_STREAM(false, false, true);

@@ -231,6 +231,13 @@ class BatchedHistoryGraph:
         """edge-type column the reference selects with ``reverse`` (RGCN.py:80-85)."""
         return self.col_type_o if reverse else self.col_type_s
 
+    def hot_rel(self, reverse):
+        """The dataset's most frequent relation ids of that type column (device int32, most frequent first) when the graph
+        came from a GraphStore, else None: the batch-scale gather keeps those relations' rows in shared memory
+        (renet_rgcn_gather_hot); without a list every CTA ranks the relations of its own edges."""
+        hot = getattr(self, 'hot', None)
+        return None if hot is None else hot[bool(reverse)]
+
     def coo_dst(self):
         if 'dst' not in self._bwd:
             self.E          # device-assembled batch: resolve the asynchronous edge count first (trims col_* to E entries)
@@ -279,6 +286,7 @@ class ReadoutSubgraph:
         dev = g.device
         S = int(readout.numel())
         self.device, self.N, self.N_src, self.reverse = dev, S, g.N, bool(reverse)
+        self._hot = g.hot_rel(reverse)
         self.E_cap = int(g.col_src.numel())
         i32 = torch.empty(3 * S + (S + 1) + 2 * self.E_cap + 2, dtype=torch.int32, device=dev)
         o = 0
@@ -325,6 +333,10 @@ class ReadoutSubgraph:
     @property
     def E_launch(self):
         return self.E_cap
+
+    def hot_rel(self, reverse):
+        assert bool(reverse) == self.reverse
+        return self._hot
 
     def col_type(self, reverse):
         if bool(reverse) != self.reverse:

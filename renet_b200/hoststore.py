@@ -65,6 +65,22 @@ class GraphStore:
                                       type_o=up(self.type_o))
         return d
 
+    def hot_relations(self, device, n=128):
+        """{reverse: device int32 [<= n]}: the relation ids of the type_s (reverse False) / type_o (True) column ranked by
+        their frequency over the whole graph_dict.  Relation frequencies are a property of the dataset, so this is
+        computed once; the batch-scale gather keeps the first few dozen of these relations' rows in shared memory."""
+        key = ('hot', str(torch.device(device)), int(n))
+        d = self._dev.get(key)
+        if d is None:
+            d = {}
+            for rev, col in ((False, self.type_s), (True, self.type_o)):
+                freq = np.bincount(col.astype(np.int64), minlength=self.num_types)
+                order = np.argsort(-freq, kind='stable')
+                order = order[freq[order] > 0][:n].astype(np.int32)
+                d[rev] = torch.from_numpy(np.ascontiguousarray(order)).to(device)
+            self._dev[key] = d
+        return d
+
     def __getitem__(self, t):
         return self.graph_dict[t]
 
@@ -416,6 +432,7 @@ def _upload_plan(view, buf, r, device):
     g._bwd = {}
     g.G, g.comp = r['G'], None
     g.seq_len_dev = d['seq_len']
+    g.hot = gs.hot_relations(device)
     g._keep = (blob, dev)
     with torch.cuda.stream(ls):
         rev = getattr(view.store, 'reverse', None)
@@ -493,6 +510,7 @@ def _upload(view, buf, r, device):
     g.comp = {False: (d['comp_ptr'], d['comp_order'], d['rel_slot_s'], d['hot_s'], r['n_hot_s']),
               True: (d['comp_ptr'], d['comp_order'], d['rel_slot_o'], d['hot_o'], r['n_hot_o'])}
     g.seq_len_dev = d['seq_len']
+    g.hot = view.store.gs.hot_relations(device)
     hb.graph = g
     hb.readout, hb.row_glob, hb.row_seq = d['readout'], d['row_comp'], d['row_seq']
     hb.seq_start, hb.packed_row = d['seq_start'], d['packed_row']

@@ -81,11 +81,12 @@ class _GatherFn(torch.autograd.Function):
             if out is loop:
                 ctx.mark_dirty(loop)
         d_in = H.shape[1]
-        rc = L.renet_rgcn_gather(_lib.ptr(H), _lib.ptr(h_index), _lib.ptr(W), _lib.ptr(g.row_ptr),
-                                 _lib.ptr(g.col_src), _lib.ptr(g.col_type(reverse)), _lib.ptr(g.norm),
-                                 _lib.ptr(out), g.N, g.E_launch, d_in, d_out, num_bases, W.shape[0], int(relu),
-                                 int(loop is not None), _lib.stream())
-        _lib.check(rc, 'renet_rgcn_gather')
+        hot = g.hot_rel(reverse)       # the dataset's relation ranking when the graph came from a GraphStore
+        rc = L.renet_rgcn_gather_hot(_lib.ptr(H), _lib.ptr(h_index), _lib.ptr(W), _lib.ptr(g.row_ptr),
+                                     _lib.ptr(g.col_src), _lib.ptr(g.col_type(reverse)), _lib.ptr(g.norm),
+                                     _lib.ptr(out), g.N, g.E_launch, d_in, d_out, num_bases, W.shape[0], int(relu),
+                                     int(loop is not None), _lib.ptr(hot), 0 if hot is None else hot.numel(), _lib.stream())
+        _lib.check(rc, 'renet_rgcn_gather_hot')
         ctx.save_for_backward(H, W, out)
         ctx.g, ctx.reverse, ctx.relu, ctx.nb, ctx.h_index, ctx.has_loop = g, reverse, relu, num_bases, h_index, loop is not None
         return out

@@ -37,10 +37,23 @@ peak = 6562.6
 kernel = os.environ.get('RENET_GATHER_KERNEL', 'auto')
 
 
+# RENET_HOT_LIST=1: pass the dataset's relation ranking (all of graph_dict's type_s columns) instead of per-CTA ranking
+hot = None
+if os.environ.get('RENET_HOT_LIST', '0') == '1':
+    freq = np.zeros(R2, dtype=np.int64)
+    for gg in tkg.graph_dict.values():
+        freq += np.bincount(np.asarray(gg.type_s, dtype=np.int64), minlength=R2)
+    hot = torch.from_numpy(np.argsort(-freq, kind='stable')[:128].astype(np.int32)).to(dev)
+
+
 def call(hb, g, H, out, layer1):
     Hin, idx = (ent, g.node_ent) if layer1 else (H, None)
-    rc = L.renet_rgcn_gather(P(Hin), P(idx), P(W), P(g.row_ptr), P(g.col_src), P(g.col_type_s), P(g.norm), P(out),
-                             g.N, g.E, 200, 200, 100, R2, 1, 1, stream)
+    if hot is None:
+        rc = L.renet_rgcn_gather(P(Hin), P(idx), P(W), P(g.row_ptr), P(g.col_src), P(g.col_type_s), P(g.norm), P(out),
+                                 g.N, g.E, 200, 200, 100, R2, 1, 1, stream)
+    else:
+        rc = L.renet_rgcn_gather_hot(P(Hin), P(idx), P(W), P(g.row_ptr), P(g.col_src), P(g.col_type_s), P(g.norm), P(out),
+                                     g.N, g.E, 200, 200, 100, R2, 1, 1, P(hot), hot.numel(), stream)
     _lib.check(rc, 'renet_rgcn_gather')
 
 
