@@ -146,9 +146,23 @@ static int launch_stream_cfg(const float* H, const int32_t* h_index, const float
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  rgcn_gather_stream_kernel<RELU, HAS_LOOP, INDEXED, false, Cfg><<<kNumSMs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
-      H, h_index, W, row_ptr, col_src, col_type, norm, Hout, N, R2, hot_rel, n_hot, E_hint, g_stream_dbg);
-  RENET_CHECK_LAUNCH("rgcn_gather_stream_kernel");
+  // programmatic stream serialisation: the grid may be scheduled while the previous kernel of the stream (the self-loop
+  // GEMM, which calls griddepcontrol.launch_dependents) is still running; the kernel's griddepcontrol.wait orders every
+  // access to that kernel's results
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kNumSMs);
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  long long* dbg = g_stream_dbg;
+  RENET_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rgcn_gather_stream_kernel<RELU, HAS_LOOP, INDEXED, false, Cfg>, H, h_index, W, row_ptr,
+                                      col_src, col_type, norm, Hout, N, R2, hot_rel, n_hot, E_hint, dbg));
+  count_launch();
   return RENET_OK;
 }
 
@@ -159,9 +173,8 @@ static int launch_stream(const float* H, const int32_t* h_index, const float* W,
 #define RENET_ST(...) return launch_stream_cfg<RELU, HAS_LOOP, INDEXED, __VA_ARGS__>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, N, R2, hot_rel, n_hot, E_hint, stream)
   if (RELU && HAS_LOOP) {               // experiment configurations exist for the layer-1 shape only (RENET_STREAM_CFG)
     switch (stream_cfg_choice()) {
-      case 1: RENET_ST(StCfg<24, 2, 44, false>);
-      case 2: RENET_ST(StCfg<28, 2, 31, false>);
-      case 3: RENET_ST(StCfg<16, 4, 31, false>);
+      case 1: RENET_ST(StCfg<28, 2, 31, false>);
+      case 2: RENET_ST(StCfg<24, 2, 44, false>);
       default: break;
     }
   }

@@ -23,10 +23,12 @@
 //   * the running destination's sum stays in registers (edges are destination-sorted: a segmented reduction); a
 //     destination that starts and ends inside the warp's range goes straight from registers through the fused
 //     norm / self-loop / activation epilogue to global memory; one cut by a warp boundary is handed over through a
-//     per-warp head slot + flag in shared memory and finished by the warp that started it, in edge order -- no atomics,
+//     per-warp head slot + mbarrier in shared memory and finished by the warp that started it, in edge order -- no atomics,
 //     bitwise reproducible (which relations are hot only changes where a row is read from, never a value).
 // The same body is the backward dH kernel (BWD: reversed CSR, transposed blocks, per-edge scale norm[dst], dH += sum).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -48,10 +50,11 @@ struct StCfg {
   static constexpr int kOffSlotOf = kOffRp + kStRpCap * 4;                  // [kStMaxR2] uint8: 1 + hot slot, 0 = cold
   static constexpr int kOffIdx = kOffSlotOf + kStMaxR2;                     // [warps][2][32] int2 {source row, relation | w_off16 << 16}
   static constexpr int kOffSc = kOffIdx + WARPS * 64 * 8;                   // BWD: [warps][2][32] float edge scales
-  static constexpr int kOffBars = kOffSc + (BWD ? WARPS * 64 * 4 : 0);      // [warps][D] + 1 mbarriers
-  static constexpr int kOffFlags = kOffBars + (WARPS * D + 1) * 8;          // [warps] flags + partition scratch (16) + range starts [warps + 1]
+  static constexpr int kOffBars = kOffSc + (BWD ? WARPS * 64 * 4 : 0);      // mbarriers: [warps][D] ring slots, hot rows, [warps] heads
+  static constexpr int kOffFlags = kOffBars + (WARPS * D + 1 + WARPS) * 8;  // [warps] (unused) + partition scratch (16) + range starts [warps + 1]
   static constexpr int kSmemBytes = kOffFlags + (2 * WARPS + 17) * 4;
   static_assert(WARPS >= 16 && WARPS <= 32, "stream gather: the partition search needs 512 threads");
+  static_assert(kBlk == 32, "stream gather: index blocks are 32 edges (D = 2 or 4)");
   static_assert(kSmemBytes <= 227 * 1024, "stream gather: shared memory budget");
   static_assert(WARPS * D * kStSlot >= (kStMaxR2 + 256 + 8) * 4, "stream gather: prologue scratch lives in the ring");
   static_assert(HOT <= 254 && (kOffHot + HOT * 1600) / 16 < 65536, "stream gather: hot rows are addressed by 16-bit offsets");
@@ -94,13 +97,36 @@ __device__ __forceinline__ void st_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   if (!done) mbar_wait(bar, parity);
 }
-__device__ __forceinline__ int ld_acquire_cta(const int* p) {
-  int v;
-  asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+// shared-memory loads through 32-bit shared-space addresses with the constant part as an immediate (the generic-pointer
+// versions of these made ptxas recompute warp-relative bases per edge: ~25 of 110 instructions)
+template <int OFF>
+__device__ __forceinline__ float2 st_lds_f2(uint32_t a) {
+  float2 r;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+%3];" : "=f"(r.x), "=f"(r.y) : "r"(a), "n"(OFF));
+  return r;
+}
+template <int OFF>
+__device__ __forceinline__ float4 st_lds_f4(uint32_t a) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a), "n"(OFF));
+  return r;
+}
+__device__ __forceinline__ uint32_t st_lds_u32(uint32_t a) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ uint2 st_lds_u2(uint32_t a) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t st_opaque(uint32_t v) {    // keeps a loop-invariant address in a register (no rematerialisation)
+  asm volatile("" : "+r"(v));
   return v;
 }
-__device__ __forceinline__ void st_release_cta(int* p, int v) {
-  asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+__device__ __forceinline__ void st_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 }  // namespace
@@ -136,8 +162,9 @@ rgcn_gather_stream_kernel(const float* __restrict__ X, const int32_t* __restrict
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);    // warp-uniform for the compiler
-  const int ml = min(lane, 24);                              // lanes 25..31 shadow lane 24 (broadcast reads, nothing stored)
-  const bool active = lane < 25;
+  // lane l owns the 2x2 blocks l, l + 32, l + 64 and -- lanes 0..3 only -- 96 + l: three full 32-lane rounds and one
+  // four-lane round per row, i.e. 20 shared-memory wavefronts per edge instead of the 24 of a 25-lane x 4 mapping
+  const bool tail4 = lane < 4;
   const bool use_hot = R2 > 0 && R2 <= kStMaxR2 && Cfg::kHot > 0;
   const bool given_hot = use_hot && hot_rel != nullptr;
   // The prologue is a chain of dependent reads (edge count -> two search rounds -> row_ptr slice -> edge indices -> row
@@ -157,12 +184,14 @@ rgcn_gather_stream_kernel(const float* __restrict__ X, const int32_t* __restrict
   }
   const int E = __ldg(row_ptr + N);
   const uint32_t hot_bar = smem_u32(bars + kStWarps * D);
+  const uint32_t head_bar0 = hot_bar + 8;                  // [warps]: "this warp's head slot is written"
 
   if (tid < 16) s_part[tid] = 0;
   if (tid < kStWarps) flags[tid] = 0;
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < D; ++k) mbar_init(smem_u32(bars + warp * D + k), 1);
+    mbar_init(head_bar0 + warp * 8, 1);
     if (warp == 0) mbar_init(hot_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -345,20 +374,24 @@ rgcn_gather_stream_kernel(const float* __restrict__ X, const int32_t* __restrict
   block_stage(0);
   block_load(1);
 
-  const uint32_t ring = smem_u32(st_smem + Cfg::kOffRing + warp * D * kStSlot);
-  const uint32_t bar0 = smem_u32(bars + warp * D);
+  const uint32_t ring = st_opaque(smem_u32(st_smem + Cfg::kOffRing + warp * D * kStSlot));
+  const uint32_t bar0 = st_opaque(smem_u32(bars + warp * D));
+  const uint32_t idx_a = st_opaque(smem_u32(my_idx));        // entry of local edge k: idx_a + (k & 63) * 8
   // copies of local edge k into ring slot `slot` (both warp-uniform)
   auto issue = [&](int k, int slot) {
-    const int b = k / kBlk;
-    const int2 ix = my_idx[(b & 1) * 32 + (k - b * kBlk)];
     if (st_elect_one()) {
+      const uint2 ix = st_lds_u2(idx_a + (((uint32_t)k & 63u) << 3));
       const bool cold = (ix.y >> 16) == 0;
       const uint32_t bar = bar0 + slot * 8, dst = ring + slot * kStSlot;
       st_expect_tx(bar, cold ? 2400u : 800u);
-      st_bulk_g2s(dst, X + (int64_t)ix.x * 200, 800, bar);
-      if (cold) st_bulk_g2s(dst + 800, W + (int64_t)(ix.y & 0xffff) * 400, 1600, bar);
+      st_bulk_g2s(dst, X + (int64_t)(int)ix.x * 200, 800, bar);
+      if (cold) st_bulk_g2s(dst + 800, W + (int64_t)(ix.y & 0xffffu) * 400, 1600, bar);
     }
   };
+  // Everything above read graph structure, weights and the relation ranking only.  From here on the kernel touches what
+  // the previous kernel in the stream produced (the self-loop rows in Hout; layer 2's input rows): with programmatic
+  // stream serialisation (see the launchers) the prologue above overlaps that kernel's tail and launch latency.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 #pragma unroll
   for (int k = 0; k < D; ++k)
     if (k < n) issue(k, k);
@@ -390,33 +423,33 @@ rgcn_gather_stream_kernel(const float* __restrict__ X, const int32_t* __restrict
     if (v < A_next) {
       if (HAS_LOOP) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) l[k] = *reinterpret_cast<const float2*>(Hout + (int64_t)v * 200 + 2 * (ml + 25 * k));
+        for (int k = 0; k < 4; ++k)
+          if (k < 3 || tail4) l[k] = *reinterpret_cast<const float2*>(Hout + (int64_t)v * 200 + 2 * (lane + 32 * k));
       }
       if (!BWD) nr = __ldg(norm + v);
     }
   };
   auto epilogue = [&](int v) {         // registers -> global, fused norm / self-loop / activation
-    if (active) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 4; ++k) {
+      if (k < 3 || tail4) {
         float2 o = make_float2(acc[2 * k], acc[2 * k + 1]);
         if (!BWD) { o.x *= nrm; o.y *= nrm; }
         if (HAS_LOOP) { o.x += lp[k].x; o.y += lp[k].y; }
         if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
-        *reinterpret_cast<float2*>(Hout + (int64_t)v * 200 + 2 * (lane + 25 * k)) = o;
+        *reinterpret_cast<float2*>(Hout + (int64_t)v * 200 + 2 * (lane + 32 * k)) = o;
       }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   };
   auto publish_head = [&]() {          // partial sum of a destination an earlier warp started
-    if (active) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        *reinterpret_cast<float2*>(heads + warp * 200 + 2 * (lane + 25 * k)) = make_float2(acc[2 * k], acc[2 * k + 1]);
-    }
+    for (int k = 0; k < 4; ++k)
+      if (k < 3 || tail4)
+        *reinterpret_cast<float2*>(heads + warp * 200 + 2 * (lane + 32 * k)) = make_float2(acc[2 * k], acc[2 * k + 1]);
     __syncwarp();
-    if (lane == 0) st_release_cta(flags + warp, 1);
+    if (lane == 0) st_arrive(head_bar0 + warp * 8);        // release: the head slot is visible to whoever observes the phase
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   };
@@ -438,42 +471,56 @@ rgcn_gather_stream_kernel(const float* __restrict__ X, const int32_t* __restrict
   fetch_dest(cur + 1, lp_n, nrm_n);
 
   if (use_hot) mbar_wait(hot_bar, 0);
-  const uint8_t* my_ring = st_smem + Cfg::kOffRing + warp * D * kStSlot;
+  const uint32_t ring_l8 = st_opaque(ring + 8 * lane), ring_l16 = st_opaque(ring + 800 + 16 * lane);
+  const uint32_t smem_l16 = st_opaque(smem_u32(st_smem) + 16 * lane);
+  const uint32_t sc_a = BWD ? st_opaque(smem_u32(my_sc)) : 0u;
   uint32_t parity = 0;
+  // index blocks: load -> dependent loads -> stage, spread over the block so that no load is waited for
+  constexpr int kP1 = (kBlk / D / 3) * D, kP2 = (2 * (kBlk / D) / 3) * D;
+  int phase_at = kP1, phase = 0, blk = 0;
   const long long t_loop = dbg ? clock64() : 0;
   for (int g = 0; g < n; g += D) {     // one pass over the ring: slot numbers are compile-time constants
-    // index blocks: load -> dependent loads -> stage, spread over the block so that no load is waited for
-    const int pos = g % kBlk, blk = g / kBlk;
-    if (pos == 0 && g > 0) block_load(blk + 1);
-    if (pos == (kBlk / D / 3) * D) block_gather(blk + 1);
-    if (pos == (2 * (kBlk / D) / 3) * D) block_stage(blk + 1);
-#pragma unroll
-    for (int slot = 0; slot < D; ++slot) {
+    if (g == phase_at) {
+      if (phase == 0) { block_gather(blk + 1); phase_at += kP2 - kP1; phase = 1; }
+      else if (phase == 1) { block_stage(blk + 1); phase_at += kBlk - kP2; phase = 2; }
+      else { ++blk; block_load(blk + 1); phase_at += kP1; phase = 0; }
+    }
+    auto do_slot = [&](auto slot_c) {
+      constexpr int slot = decltype(slot_c)::value;
       const int i = g + slot;
       if (i < n) {
         while (e0 + i >= cur_end) advance();       // warp-uniform: the running destination is complete
-        const int ib = (blk & 1) * 32 + pos + slot;
-        const uint32_t woff16 = (uint32_t)my_idx[ib].y >> 16;
-        const uint8_t* sp = my_ring + slot * kStSlot;
-        const uint8_t* wp = woff16 ? st_smem + woff16 * 16 : sp + 800;
-        const float sc = BWD ? my_sc[ib] : 1.f;
+        const uint32_t woff16 = st_lds_u32(idx_a + (((uint32_t)i & 63u) << 3) + 4) >> 16;
+        const uint32_t wa = woff16 ? smem_l16 + (woff16 << 4) : ring_l16 + slot * kStSlot;
+        const float sc = BWD ? __uint_as_float(st_lds_u32(sc_a + (((uint32_t)i & 63u) << 2))) : 1.f;
         st_wait(bar0 + slot * 8, parity);
+        float2 h[4];
+        float4 w[4];
+        h[0] = st_lds_f2<slot * kStSlot>(ring_l8);       h[1] = st_lds_f2<slot * kStSlot + 256>(ring_l8);
+        h[2] = st_lds_f2<slot * kStSlot + 512>(ring_l8);
+        w[0] = st_lds_f4<0>(wa); w[1] = st_lds_f4<512>(wa); w[2] = st_lds_f4<1024>(wa);
+        h[3] = make_float2(0.f, 0.f); w[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tail4) { h[3] = st_lds_f2<slot * kStSlot + 768>(ring_l8); w[3] = st_lds_f4<1536>(wa); }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float2 h = *reinterpret_cast<const float2*>(sp + 8 * (ml + 25 * k));
-          const float4 w = *reinterpret_cast<const float4*>(wp + 16 * (ml + 25 * k));
-          const float x = BWD ? h.x * sc : h.x, y = BWD ? h.y * sc : h.y;
+          const float x = BWD ? h[k].x * sc : h[k].x, y = BWD ? h[k].y * sc : h[k].y;
           if (!BWD) {                  // out[j] += sum_i in[i] * W[i][j]
-            acc[2 * k] = fmaf(x, w.x, fmaf(y, w.z, acc[2 * k]));
-            acc[2 * k + 1] = fmaf(x, w.y, fmaf(y, w.w, acc[2 * k + 1]));
+            acc[2 * k] = fmaf(x, w[k].x, fmaf(y, w[k].z, acc[2 * k]));
+            acc[2 * k + 1] = fmaf(x, w[k].y, fmaf(y, w[k].w, acc[2 * k + 1]));
           } else {                     // din[i] += sum_j W[i][j] * g[j]
-            acc[2 * k] = fmaf(x, w.x, fmaf(y, w.y, acc[2 * k]));
-            acc[2 * k + 1] = fmaf(x, w.z, fmaf(y, w.w, acc[2 * k + 1]));
+            acc[2 * k] = fmaf(x, w[k].x, fmaf(y, w[k].y, acc[2 * k]));
+            acc[2 * k + 1] = fmaf(x, w[k].z, fmaf(y, w[k].w, acc[2 * k + 1]));
           }
         }
         __syncwarp();                  // every lane has consumed the slot (the FMAs depend on the loads)
         if (i + D < n) issue(i + D, slot);
       }
+    };
+    do_slot(std::integral_constant<int, 0>{});
+    do_slot(std::integral_constant<int, 1>{});
+    if constexpr (D == 4) {
+      do_slot(std::integral_constant<int, 2>{});
+      do_slot(std::integral_constant<int, 3>{});
     }
     parity ^= 1u;
   }
@@ -489,17 +536,13 @@ rgcn_gather_stream_kernel(const float* __restrict__ X, const int32_t* __restrict
       // this warp started `cur`; later warps hold the rest of its edges: add their heads in warp (= edge) order
       for (int k = warp + 1; k < kStWarps && s_e0[k] < cur_end; ++k) {
         if (s_e0[k + 1] == s_e0[k]) continue;      // empty range: no head
-        if (lane == 0) {
-          int spins = 0;
-          while (ld_acquire_cta(flags + k) == 0) {
-            if (++spins > (1 << 24)) __trap();
-          }
-        }
-        __syncwarp();
+        mbar_wait(head_bar0 + k * 8, 0);           // acquire (bounded spin: a lost head traps instead of hanging)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float2 hv = *reinterpret_cast<const float2*>(heads + k * 200 + 2 * (ml + 25 * q));
-          acc[2 * q] += hv.x; acc[2 * q + 1] += hv.y;
+          if (q < 3 || tail4) {
+            const float2 hv = *reinterpret_cast<const float2*>(heads + k * 200 + 2 * (lane + 32 * q));
+            acc[2 * q] += hv.x; acc[2 * q + 1] += hv.y;
+          }
         }
       }
       epilogue(cur);
@@ -516,10 +559,10 @@ rgcn_gather_stream_kernel(const float* __restrict__ X, const int32_t* __restrict
     while (m) {
       const int u = base + __ffs(m) - 1;
       m &= m - 1;
-      if (active) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float* op = Hout + (int64_t)u * 200 + 2 * (lane + 25 * k);
+      for (int k = 0; k < 4; ++k) {
+        if (k < 3 || tail4) {
+          float* op = Hout + (int64_t)u * 200 + 2 * (lane + 32 * k);
           float2 o = make_float2(0.f, 0.f);
           if (HAS_LOOP) o = *reinterpret_cast<const float2*>(op);
           if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); }
