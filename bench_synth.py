@@ -70,6 +70,7 @@ def run_synth1m(args, WORKLOAD, METRIC, UNIT, ClockSampler, measured_peak_gbs):
     g = _G()
     g.device, g.N, g.row_ptr, g.col_src, g.norm = dev, N, row_ptr, col_src, norm
     g.col_type = lambda reverse: col_type
+    g.hot_rel = lambda reverse: None
     sub = ReadoutSubgraph(g, sh['readout'], False)
     U, E2 = sub.sizes()
     torch.manual_seed(999)

@@ -468,6 +468,62 @@ def gen_global_tiny(ns):
     print('global_tiny.npz: losses', blob['pool1/subj/loss'], blob['pool1/obj/loss'], blob['pool0/subj/loss'])
 
 
+def gen_renet_eval_global(ns):
+    """The reference's whole test flow with its OWN global model (test.py:41-150): RENet_global (deterministic parameters)
+    produces global_emb for the training timestamps (pretrain.py:92) and drives the roll-over at test time; RENet
+    (h = 200, num_bases = 100: the shape the CUDA fast path serves; the reference hard-codes 100 bases in the global
+    aggregator) is evaluated with evaluate_filter over the test split of the tiny stream.  Stored: the global_emb table,
+    every filtered rank, and MRR / MR / Hits@1/3/10 as test.py prints them."""
+    from oracle import restate
+    tiny = np.load(os.path.join(OUT, 'renet_tiny.npz'))
+    quads = tiny['quads'].astype(np.int64)
+    num_e, R, h, nb, seed = int(tiny['num_e']), int(tiny['R']), 200, 100, 31
+    times = np.unique(quads[:, 3])
+    t_valid, t_test = times[-4], times[-2]
+    S, ST, O, OT = restate.build_history(quads, num_e)
+    split = lambda lo, hi: np.flatnonzero((quads[:, 3] >= lo) & (quads[:, 3] < hi))   # noqa: E731
+    tr, va, te = split(0, t_valid), split(t_valid, t_test), split(t_test, times[-1] + 1)
+    pick = lambda L, idx: [L[i] for i in idx]                                           # noqa: E731
+    with ref_loader.cpu_patches():
+        gd = {int(t): ns.utils.get_big_graph(quads[quads[:, 3] == t][:, :3], R) for t in times}
+        gm = ns.global_model.RENet_global(num_e, h, R, dropout=0, model=3, seq_len=10, num_k=5, maxpool=1)
+        gshapes = {k: tuple(v.shape) for k, v in gm.state_dict().items()}
+        gm.load_state_dict(det_params(gshapes, seed + 1), strict=True)
+        gm.eval()
+        m = ns.model.RENet(num_e, h, R, dropout=0, model=0, seq_len=10, num_k=5)
+        m.load_state_dict(det_params(RENET_SHAPES(num_e, h, R, nb), seed), strict=True)
+        m.eval()
+        train_times = [int(t) for t in np.unique(quads[tr][:, 3])]
+        with torch.no_grad():
+            ge = gm.get_global_emb(train_times, gd)
+        m.global_emb = ge
+        res = {'global_emb_keys': np.asarray(sorted(ge)), 'global_emb': np.stack([ge[k].view(-1).numpy() for k in sorted(ge)])}
+        m.graph_dict = gd
+        m.init_history(quads[tr], (pick(S, tr), pick(ST, tr)), (pick(O, tr), pick(OT, tr)),
+                       quads[va], (pick(S, va), pick(ST, va)), (pick(O, va), pick(OT, va)),
+                       quads[te], (pick(S, te), pick(ST, te)), (pick(O, te), pick(OT, te)))
+        for ee in range(num_e):                                     # test.py:100-106
+            while len(m.s_hist_test[ee]) > 10:
+                m.s_hist_test[ee].pop(0); m.s_hist_test_t[ee].pop(0)
+            while len(m.o_hist_test[ee]) > 10:
+                m.o_hist_test[ee].pop(0); m.o_hist_test_t[ee].pop(0)
+        m.latest_time = torch.tensor(int(t_test))
+        allq = torch.from_numpy(quads)
+        torch.manual_seed(4321)
+        ranks, losses = [], []
+        with torch.no_grad():
+            for i in te:                                            # test.py:113-136
+                fr, loss = m.evaluate_filter(torch.from_numpy(quads[i]), (S[i], ST[i]), (O[i], OT[i]), gm, allq)
+                ranks.append(fr); losses.append(loss.item())
+    ranks = np.concatenate(ranks)
+    res.update(ranks=ranks, loss=np.asarray(losses), mrr=np.mean(1.0 / ranks), mr=np.mean(ranks),
+               hits=np.asarray([np.mean(ranks <= k) for k in (1, 3, 10)]), tr=tr, va=va, te=te, seed=seed, h=h, nb=nb, num_k=5,
+               gshape_keys=np.asarray(sorted(gshapes)),
+               gshape_vals=np.asarray([list(gshapes[k]) + [0] * (2 - len(gshapes[k])) for k in sorted(gshapes)]))
+    np.savez_compressed(os.path.join(OUT, 'renet_eval_global.npz'), **res)
+    print('renet_eval_global.npz: %d ranks, MRR %.6f MR %.3f Hits@1/3/10 %s' % (len(ranks), res['mrr'], res['mr'], res['hits']))
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
@@ -479,3 +535,4 @@ if __name__ == '__main__':
     gen_renet_eval_tiny(ns)
     gen_aggregator_predict(ns)
     gen_global_tiny(ns)
+    gen_renet_eval_global(ns)

@@ -74,10 +74,11 @@ int sgemm_tn(const float* A, const int32_t* a_index, int64_t lda, const float* B
 int sgemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
              int64_t M, int32_t N, int32_t K, bool accumulate, cudaStream_t stream);
 
-// 0 = automatic, 1 = tile, 2 = sliced, 3 = stream (RENET_GATHER_KERNEL=tile|sliced|stream; rgcn_fwd.cu)
+// 0 = automatic, 1 = tile, 3 = stream (RENET_GATHER_KERNEL=tile|stream; rgcn_fwd.cu)
 int gather_kernel_choice();
 constexpr int64_t kStreamMinEdges = 16384;   // below this a persistent 148-CTA launch costs more than the tile kernel
 constexpr int64_t kStreamMinNodes = 16384;
+constexpr int64_t kStreamMaxNodes = 98304;    // 79 MB of fp32 features: beyond this the source rows come from HBM, not L2
 bool gather_use_stream(int64_t E, int64_t N);
 void set_stream_debug_buffer(long long* p);   // debug: per-warp time stamps of the stream kernel (rgcn_fwd.cu)          // the stream kernel (rgcn_stream.cuh) serves this edge count
 

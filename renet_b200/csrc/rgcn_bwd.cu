@@ -12,7 +12,6 @@
 // flushes once per relation change with 128-bit vector REDs.
 #include "common.cuh"
 #include "rgcn_tile.cuh"
-#include "rgcn_sliced.cuh"
 #include "rgcn_stream.cuh"
 
 namespace renet {
@@ -278,28 +277,7 @@ int launch_rgcn_bwd(const float* H, const int32_t* h_index, const float* W, cons
                     ((reinterpret_cast<uintptr_t>(H) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(dH) |
                       reinterpret_cast<uintptr_t>(dW) | reinterpret_cast<uintptr_t>(P)) & 15) == 0;
   if (fast) {
-    if (R2 <= kSlMaxR2 && gather_kernel_choice() == 2) {
-      // batch scale: the sliced persistent kernel on the reversed graph (transposed blocks, per-edge scale norm[dst]):
-      // relation rows from shared memory, no atomics, bitwise reproducible dH
-      static bool attr_done = false;
-      if (!attr_done) {
-        RENET_CHECK_CUDA(cudaFuncSetAttribute(rgcn_gather_sliced_kernel<false, true, false, true>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sliced_smem_bytes(kSlMaxR2)));
-        RENET_CHECK_CUDA(cudaFuncSetAttribute(rgcn_gather_sliced_kernel<false, false, false, true>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sliced_smem_bytes(kSlMaxR2)));
-        attr_done = true;
-      }
-      const size_t smem = sliced_smem_bytes(R2);
-      CUtensorMap w_map;
-      if ((rc = sliced_make_tmap(W, R2, &w_map))) return rc;
-      if (Wloop != nullptr)
-        rgcn_gather_sliced_kernel<false, true, false, true><<<kNumSMs, kSlThreads, smem, stream>>>(
-            P, nullptr, w_map, t_row_ptr, t_col_dst, t_col_type, norm, dH, (int)N, R2);
-      else
-        rgcn_gather_sliced_kernel<false, false, false, true><<<kNumSMs, kSlThreads, smem, stream>>>(
-            P, nullptr, w_map, t_row_ptr, t_col_dst, t_col_type, norm, dH, (int)N, R2);
-      RENET_CHECK_LAUNCH("rgcn_gather_sliced_kernel(bwd)");
-    } else if (E > 0 && gather_use_stream(E, N)) {
+    if (E > 0 && gather_use_stream(E, N)) {
       // batch scale: the persistent bulk-copy kernel on the reversed graph -- no atomics, bitwise reproducible dH
       static bool attr_done = false;
       if (!attr_done) {

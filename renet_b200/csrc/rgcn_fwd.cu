@@ -14,15 +14,14 @@
 
 #include "common.cuh"
 #include "rgcn_tile.cuh"
-#include "rgcn_sliced.cuh"
 #include "rgcn_stream.cuh"
 
 namespace renet {
 namespace {
 
-// Tile kernel (round 1; rgcn_tile.cuh): one CTA per 16 destinations.  Still the path for small graphs (inference on a
-// handful of sub-graphs, where staging a slice of the relation table into 148 SMs would cost more than the work), for
-// relation tables too large for the sliced kernel's shared memory, and for DGL's edge-less pass-through.
+// Tile kernel (round 1; rgcn_tile.cuh): one CTA per 16 destinations.  The path for small graphs (inference on a handful of
+// sub-graphs, the read-out sub-graph of layer 2: a persistent 148-CTA launch would cost more than the work) and for DGL's
+// edge-less pass-through; at batch scale the persistent kernel of rgcn_stream.cuh takes over (gather_use_stream).
 template <bool RELU, bool HAS_LOOP, bool INDEXED, int NODES = kTileNodes>
 __global__ void __launch_bounds__(kTileWarps * 32, 768 / (kTileWarps * 32))
 rgcn_gather_d200_kernel(const float* __restrict__ H, const int32_t* __restrict__ h_index,
@@ -102,15 +101,14 @@ __global__ void rgcn_gather_generic_kernel(const float* __restrict__ H, const in
 }  // namespace
 
 // Which kernel serves the d=200 shape: 0 = automatic (the stream kernel at batch scale, the tile kernel for small graphs),
-// 1 = tile, 2 = sliced (whenever its shared memory allows), 3 = stream.  RENET_GATHER_KERNEL=tile|sliced|stream picks one per
-// process for A/B measurements (tools/bench_gather.py); results agree to fp32 summation order.
+// 1 = tile, 3 = stream.  RENET_GATHER_KERNEL=tile|stream picks one per process for A/B measurements
+// (tools/bench_gather.py); results agree to fp32 summation order.
 int gather_kernel_choice() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("RENET_GATHER_KERNEL");
     v = 0;
     if (e && e[0] == 't') v = 1;
-    else if (e && e[0] == 's' && e[1] == 'l') v = 2;
     else if (e && e[0] == 's') v = 3;
   }
   return v;
@@ -118,9 +116,12 @@ int gather_kernel_choice() {
 bool gather_use_stream(int64_t E, int64_t N) {
   // E may be an upper bound (device-assembled batches and read-out sub-graphs pass their capacity), so the destination
   // count decides with it: the persistent kernel pays ~5 us of prologue per launch, which a few thousand destinations'
-  // worth of edges does not amortise (read-out sub-graph of an ICEWS18 batch: tile kernel 26 us, stream kernel 43 us)
+  // worth of edges does not amortise (read-out sub-graph of an ICEWS18 batch: tile kernel 26 us, stream kernel 43 us).
+  // And it is built for feature matrices that live in L2 (ICEWS18 27 MB: 41 vs 50 us; GDELT 83 vs 119 us): with two rows
+  // in flight per warp it cannot cover HBM latency, so when the features exceed L2 (synthetic 1 M-entity shard, 800 MB:
+  // tile kernel 4.65 ms = 0.90 of the HBM roofline, stream kernel 17 ms) the tile kernel stays
   const int c = gather_kernel_choice();
-  return c == 3 || (c == 0 && E >= kStreamMinEdges && N >= kStreamMinNodes);
+  return c == 3 || (c == 0 && E >= kStreamMinEdges && N >= kStreamMinNodes && N <= kStreamMaxNodes);
 }
 
 // debug hook (tools/stream_timeline.py): per-warp time stamps of the next stream-kernel launches; never set in production
@@ -182,26 +183,6 @@ static int launch_stream(const float* H, const int32_t* h_index, const float* W,
 #undef RENET_ST
 }
 
-template <bool RELU, bool HAS_LOOP, bool INDEXED>
-static int launch_sliced(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
-                         const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout, int N, int R2,
-                         cudaStream_t stream) {
-  static bool attr_done = false;        // one device per process (one process per GPU)
-  const size_t smem = sliced_smem_bytes(R2);
-  if (!attr_done) {
-    RENET_CHECK_CUDA(cudaFuncSetAttribute(rgcn_gather_sliced_kernel<RELU, HAS_LOOP, INDEXED, false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sliced_smem_bytes(kSlMaxR2)));
-    attr_done = true;
-  }
-  CUtensorMap w_map;
-  int rc = sliced_make_tmap(W, R2, &w_map);
-  if (rc) return rc;
-  rgcn_gather_sliced_kernel<RELU, HAS_LOOP, INDEXED, false><<<kNumSMs, kSlThreads, smem, stream>>>(
-      H, h_index, w_map, row_ptr, col_src, col_type, norm, Hout, N, R2);
-  RENET_CHECK_LAUNCH("rgcn_gather_sliced_kernel");
-  return RENET_OK;
-}
-
 int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, const int32_t* row_ptr,
                        const int32_t* col_src, const int32_t* col_type, const float* norm, float* Hout,
                        int64_t N, int64_t E, int d_in, int d_out, int nb, int relu, int has_loop,
@@ -212,24 +193,7 @@ int launch_rgcn_gather(const float* H, const int32_t* h_index, const float* W, c
                     ((reinterpret_cast<uintptr_t>(H) | reinterpret_cast<uintptr_t>(W) |
                       reinterpret_cast<uintptr_t>(Hout)) & 15) == 0;
   if (fast) {
-    const int choice = gather_kernel_choice();
-    // E may be an upper bound (device-assembled batches pass the capacity): the sliced kernel reads row_ptr[N] itself
-    const bool sliced = !passthrough && R2 > 0 && R2 <= kSlMaxR2 && choice == 2;
     const int key = (relu ? 4 : 0) | (has_loop ? 2 : 0) | (h_index ? 1 : 0);
-    if (sliced) {
-#define RENET_LAUNCH_SLICED(R, L, I) return launch_sliced<R, L, I>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, R2, stream)
-      switch (key) {
-        case 0: RENET_LAUNCH_SLICED(false, false, false);
-        case 1: RENET_LAUNCH_SLICED(false, false, true);
-        case 2: RENET_LAUNCH_SLICED(false, true, false);
-        case 3: RENET_LAUNCH_SLICED(false, true, true);
-        case 4: RENET_LAUNCH_SLICED(true, false, false);
-        case 5: RENET_LAUNCH_SLICED(true, false, true);
-        case 6: RENET_LAUNCH_SLICED(true, true, false);
-        default: RENET_LAUNCH_SLICED(true, true, true);
-      }
-#undef RENET_LAUNCH_SLICED
-    }
     if (!passthrough && gather_use_stream(E, N)) {
 #define RENET_LAUNCH_STREAM(R, L, I) return launch_stream<R, L, I>(H, h_index, W, row_ptr, col_src, col_type, norm, Hout, (int)N, R2, hot_rel, n_hot, (int)E, stream)
       switch (key) {

@@ -286,7 +286,7 @@ class ReadoutSubgraph:
         dev = g.device
         S = int(readout.numel())
         self.device, self.N, self.N_src, self.reverse = dev, S, g.N, bool(reverse)
-        self._hot = g.hot_rel(reverse)
+        self._hot = g.hot_rel(reverse) if hasattr(g, 'hot_rel') else None
         self.E_cap = int(g.col_src.numel())
         i32 = torch.empty(3 * S + (S + 1) + 2 * self.E_cap + 2, dtype=torch.int32, device=dev)
         o = 0

@@ -202,7 +202,7 @@ def _global_table(global_emb, h, device):
     if (hit is None or hit[0] is not global_emb or len(hit[1]) != len(vals) or hit[3].device != torch.device(device)
             or not all(map(operator.is_, vals, hit[1]))):
         keys = np.asarray(sorted(int(t) for t in global_emb.keys()), dtype=np.int64)
-        table = torch.stack([global_emb[int(t)].reshape(-1) for t in keys]).to(device=device, dtype=torch.float32)
+        table = torch.stack([global_emb[int(t)].reshape(-1).to(device=device, dtype=torch.float32) for t in keys])   # entries may live on different devices
         hit = (global_emb, vals, keys, table.view(len(keys), h))
         _GLOB_CACHE.clear()
         _GLOB_CACHE[key] = hit

@@ -1,7 +1,7 @@
 """Micro-benchmark + cross-check of the fused gather kernels on dataset-shaped batches (run on the GPU box).
 
     RENET_GATHER_KERNEL=tile   python tools/bench_gather.py [icews18|gdelt|icews14] [timestamps]
-    RENET_GATHER_KERNEL=stream python tools/bench_gather.py ...        (or sliced)
+    RENET_GATHER_KERNEL=stream python tools/bench_gather.py ...
 
 The kernel choice is read once per process (environment), so an A/B is two runs; each run also writes a checksum of the
 layer outputs so the two kernels can be compared (they agree to fp32 summation order, not bit for bit)."""
