@@ -42,7 +42,7 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
                    const float* w_ih3, const float* w_hh3, const float* b_ih3, const float* b_hh3, float* hn4,
                    float* hn3, int64_t S, int64_t Q, int64_t T, int h, float* ws_base, cudaStream_t stream, float p_drop = 0.f,
                    uint64_t seed = 0, const int32_t* row_seq = nullptr, const float* ext_X4 = nullptr, int k4 = 0,
-                   const float* ext_X3 = nullptr, int k3 = 0);
+                   const float* ext_X3 = nullptr, int k3 = 0, int phase = 0);
 int64_t gru_bwd_workspace_floats(int64_t S, int64_t Q, int64_t T, int h, bool dropout = false);
 int launch_dropout_mask(uint64_t seed, uint64_t offset, int64_t n, float p, float* out, cudaStream_t stream);
 int launch_gru_bwd(const float* H2, const int32_t* readout, const int32_t* row_glob, const float* glob,
@@ -450,6 +450,32 @@ int renet_encode_fwd(const float* ent, const int32_t* node_ent, const int32_t* r
                      int32_t n_hot, void* workspace, int64_t workspace_bytes, void* stream) {
   RENET_CHECK_ARG(n_hot >= 0 && (n_hot == 0 || hot_rel != nullptr), "renet_encode_fwd: bad hot-relation list");
   if (n_hot == 0) hot_rel = nullptr;
+  // The part of the GRU that does not depend on the RGCN output -- weight packing, bias rows, the per-sequence and
+  // per-timestamp input projections: four small launches, ~110 us of latency, a handful of CTAs -- runs on a side stream
+  // underneath the two RGCN layers (fork / join by events; the side stream and its events are created on first use and
+  // live for the process: one device, one caller stream at a time, as everywhere in this library).
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  const bool gru_args_ok = S > 0 && Q > 0 && readout && row_glob && glob && rel && seq_s && seq_r && seq_len && seq_start &&
+                           host_batch_sizes && w_ih4 && w_hh4 && b_ih4 && b_hh4 && w_ih3 && w_hh3 && b_ih3 && b_hh3 && hn4 && hn3 &&
+                           workspace && workspace_bytes >= renet_gru_workspace_bytes(S, Q, T, h) &&
+                           (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && max_len >= 0 && T >= 0;
+  bool forked = false;
+  if (gru_args_ok) {
+    if (side == nullptr) {
+      RENET_CHECK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+      RENET_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      RENET_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    RENET_CHECK_CUDA(cudaEventRecord(ev_fork, (cudaStream_t)stream));
+    RENET_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+    int rc1 = launch_gru_fwd(nullptr, readout, row_glob, glob, ent, rel, seq_s, seq_r, seq_len, seq_start, host_batch_sizes, max_len,
+                             w_ih4, w_hh4, b_ih4, b_hh4, w_ih3, w_hh3, b_ih3, b_hh3, hn4, hn3, S, Q, T, h, (float*)workspace, side,
+                             0.f, 0, nullptr, nullptr, 0, nullptr, 0, 1);
+    RENET_CHECK_CUDA(cudaEventRecord(ev_join, side));
+    if (rc1) return rc1;
+    forked = true;
+  }
   // layer 1 (embedding lookup fused through node_ent, ReLU), layer 2 (linear), then read-out + both GRUs
   int rc = check_layer_args("renet_encode_fwd", ent, W1, row_ptr, norm, H1, N, E, h, h, num_bases, R2);
   if (rc) return rc;
@@ -482,6 +508,11 @@ int renet_encode_fwd(const float* ent, const int32_t* node_ent, const int32_t* r
                               stream);
     if (rc) return rc;
   }
+  if (forked) RENET_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ev_join, 0));
+  if (forked)
+    return launch_gru_fwd(H2, readout, row_glob, glob, ent, rel, seq_s, seq_r, seq_len, seq_start, host_batch_sizes, max_len, w_ih4,
+                          w_hh4, b_ih4, b_hh4, w_ih3, w_hh3, b_ih3, b_hh3, hn4, hn3, S, Q, T, h, (float*)workspace,
+                          (cudaStream_t)stream, 0.f, 0, nullptr, nullptr, 0, nullptr, 0, 2);
   return renet_gru_fwd(H2, readout, row_glob, glob, ent, rel, seq_s, seq_r, seq_len, seq_start, host_batch_sizes, max_len,
                        w_ih4, w_hh4, b_ih4, b_hh4, w_ih3, w_hh3, b_ih3, b_hh3, hn4, hn3, S, Q, T, h, workspace,
                        workspace_bytes, stream);

@@ -273,7 +273,11 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
                    int max_len, const float* w_ih4, const float* w_hh4, const float* b_ih4, const float* b_hh4,
                    const float* w_ih3, const float* w_hh3, const float* b_ih3, const float* b_hh3, float* hn4,
                    float* hn3, int64_t S, int64_t Q, int64_t T, int h, float* ws_base, cudaStream_t stream, float p_drop,
-                   uint64_t seed, const int32_t* row_seq, const float* ext_X4, int k4, const float* ext_X3, int k3) {
+                   uint64_t seed, const int32_t* row_seq, const float* ext_X4, int k4, const float* ext_X3, int k3, int phase) {
+  // phase 0: everything.  phase 1: only what does not depend on H2 (weight packing, bias rows, the per-sequence and
+  // per-timestamp projections PQ / PT); phase 2: the rest (GI and the recurrence).  renet_encode_fwd runs phase 1 on a side
+  // stream under the RGCN layers.  The split exists for the tensor-core engine without dropout; other configurations do
+  // everything in phase 2.
   // ext_X4 != nullptr: "dense" mode -- GRU(s) on caller-materialised inputs X4 [S,k4] (and X3 [S,k3], or nullptr for a single
   // GRU: the global model's GRU(h,h), global_model.py:25,49); readout / ent / rel / glob / row_glob are not used
   const bool dense = ext_X4 != nullptr;
@@ -284,6 +288,14 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
   }
   const bool dropout = p_drop > 0.f || dense;
   GruWs w = carve(ws_base, S, Q, T, h, kMaxLenWs, dropout);
+  {
+    const bool splittable = gemm_mode() == 1 && h % 4 == 0 && (3 * h) % 200 == 0 && (reinterpret_cast<uintptr_t>(ws_base) & 127) == 0 &&
+                            !dropout;
+    if (!splittable) {
+      if (phase == 1) return RENET_OK;
+      phase = 0;
+    }
+  }
   if (dense) {
     if (k4 <= 0 || k4 > 4 * h || k4 % 4 != 0 || (ext_X3 != nullptr && (k3 <= 0 || k3 > 3 * h || k3 % 4 != 0))) {
       set_error("renet_gru_dense_fwd: input widths must be multiples of 4 with k4 <= 4h, k3 <= 3h");
@@ -322,7 +334,7 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
         w.P_ent = cached + (w.P_ent - base); w.P_rel = cached + (w.P_rel - base); w.P_glob = cached + (w.P_glob - base);
         w.P_hh = cached + (w.P_hh - base); w.P_row = cached;
       }
-      if (!hit) {
+      if (!hit && phase != 2) {
         // logical B[k][n] = w[n][col_off + k]  ->  sk = 1, sn = leading dimension of w
         if ((rc = umma_pack_b(w_ih4, 1, 4 * h, 3 * h, h, w.P_row, 0, stream))) return rc;
         if ((rc = umma_pack_b(w_ih3, 1, 3 * h, 3 * h, h, w.P_row, t3, stream))) return rc;
@@ -335,10 +347,12 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
         if ((rc = umma_pack_b(w_hh3, 1, h, 3 * h, h, reinterpret_cast<uint8_t*>(w.P_hh) + w.p_hh_bytes, 0, stream))) return rc;
       }
     }
-    concat_bias_kernel<<<(6 * h + 255) / 256, 256, 0, stream>>>(b_ih4, b_ih3, w.bih, 3 * h);
-    RENET_CHECK_LAUNCH("concat_bias_kernel");
-    concat_bias_kernel<<<(6 * h + 255) / 256, 256, 0, stream>>>(b_hh4, b_hh3, w.bhh, 3 * h);
-    RENET_CHECK_LAUNCH("concat_bias_kernel");
+    if (phase != 2) {
+      concat_bias_kernel<<<(6 * h + 255) / 256, 256, 0, stream>>>(b_ih4, b_ih3, w.bih, 3 * h);
+      RENET_CHECK_LAUNCH("concat_bias_kernel");
+      concat_bias_kernel<<<(6 * h + 255) / 256, 256, 0, stream>>>(b_hh4, b_hh3, w.bhh, 3 * h);
+      RENET_CHECK_LAUNCH("concat_bias_kernel");
+    }
     if (dropout) {
       // masked (or caller-provided) inputs materialised once, projected by two GEMMs:
       // GI = [X4 @ W_ih4^T | X3 @ W_ih3^T]; PQ = b_ih, PT = 0
@@ -361,11 +375,15 @@ int launch_gru_fwd(const float* H2, const int32_t* readout, const int32_t* row_g
       RENET_CHECK_LAUNCH("fill_rows_kernel");
       RENET_CHECK_CUDA(cudaMemsetAsync(w.PT, 0, T * 6 * h * sizeof(float), stream));
     } else {
-    if ((rc = umma_gemm_prepacked(H2, readout, h, w.P_row, w.GI, 6 * h, nullptr, S, 6 * h, h, false, 1, 0, 0, 0, stream))) return rc;
-    if ((rc = umma_gemm_prepacked(ent, seq_s, h, w.P_ent, w.PQ, 6 * h, w.bih, Q, 6 * h, h, false, 1, 0, 0, 0, stream))) return rc;
-    if ((rc = umma_gemm_prepacked(rel, seq_r, h, w.P_rel, w.PQ, 6 * h, nullptr, Q, 3 * h, h, true, 1, 0, 0, 0, stream))) return rc;
-    if ((rc = umma_gemm_prepacked(glob, nullptr, h, w.P_glob, w.PT, 6 * h, nullptr, T, 6 * h, h, false, 1, 0, 0, 0, stream))) return rc;
+    if (phase != 1)
+      if ((rc = umma_gemm_prepacked(H2, readout, h, w.P_row, w.GI, 6 * h, nullptr, S, 6 * h, h, false, 1, 0, 0, 0, stream))) return rc;
+    if (phase != 2) {
+      if ((rc = umma_gemm_prepacked(ent, seq_s, h, w.P_ent, w.PQ, 6 * h, w.bih, Q, 6 * h, h, false, 1, 0, 0, 0, stream))) return rc;
+      if ((rc = umma_gemm_prepacked(rel, seq_r, h, w.P_rel, w.PQ, 6 * h, nullptr, Q, 3 * h, h, true, 1, 0, 0, 0, stream))) return rc;
+      if ((rc = umma_gemm_prepacked(glob, nullptr, h, w.P_glob, w.PT, 6 * h, nullptr, T, 6 * h, h, false, 1, 0, 0, 0, stream))) return rc;
     }
+    }
+    if (phase == 1) return RENET_OK;
     // recurrence: one persistent cooperative tensor-core kernel for all time steps and both encoders (gru_recur.cu);
     // the step-by-step loop below is the fallback for shapes it does not take
     rc = launch_gru_recur(w.GI, w.PQ, w.PT, w.bhh, row_glob, seq_start, seq_len, w_hh4, w_hh3, w.Hs, w.GH, hn4, hn3,
