@@ -653,6 +653,17 @@ def run_ours(args):
         # one full rotation over the pool of batches: the loader, the pinned pool and the caching allocator (whose block
         # sizes depend on the batch) have reached steady state before the clock starts
         w_e2e = max(len(pool) + 1, args.warmup)
+        if os.environ.get('RENET_E2E_PROFILE') == '1' and rank == 0:      # debug: where the consumer thread's time goes
+            import cProfile, pstats, io
+            run_e2e(w_e2e, 20, 0)
+            pr = cProfile.Profile()
+            pr.enable()
+            run_e2e(2, 100, 0)
+            pr.disable()
+            for key in ('tottime', 'cumulative'):
+                buf = io.StringIO()
+                pstats.Stats(pr, stream=buf).sort_stats(key).print_stats(28)
+                sys.stderr.write(buf.getvalue())
         h2d, d2h, msgs, dt = run_e2e(w_e2e, k_e2e, 0)
         tt = torch.tensor([dt, float(msgs)], device=dev, dtype=torch.float64)
         if world > 1:

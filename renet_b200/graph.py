@@ -305,10 +305,9 @@ class ReadoutSubgraph:
                                       P(self.uniq), P(self.readout_c), P(self.row_ptr), P(self.col_src), P(self._col_type),
                                       P(self.norm), P(self.counts), P(ws), nbytes, _lib.stream())
         _lib.check(rc, 'renet_readout_subgraph')
-        try:
-            host = _CNT_PINNED.pop()
-        except IndexError:
-            host = torch.empty(2, dtype=torch.int32).pin_memory()
+        if not _CNT_PINNED:
+            _lib.pinned_slots(_CNT_PINNED, 2)
+        host = _CNT_PINNED.pop()
         host.copy_(self.counts, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()

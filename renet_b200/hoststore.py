@@ -443,10 +443,9 @@ def _upload_plan(view, buf, r, device):
             sub = g.readout_sub(d['readout'], rev)
         ready = torch.cuda.Event()
         ready.record(ls)
-        try:
-            e_host = _E_PINNED.pop()
-        except IndexError:
-            e_host = torch.empty(1, dtype=torch.int32).pin_memory()
+        if not _E_PINNED:
+            _lib.pinned_slots(_E_PINNED, 1)
+        e_host = _E_PINNED.pop()
         e_host.copy_(parts['e_count'], non_blocking=True)
         e_ev = torch.cuda.Event()
         e_ev.record(ls)

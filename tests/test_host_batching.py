@@ -339,3 +339,20 @@ def test_view_from_lists_equals_numpy_path_and_store_path():
     t0 = int(gs.times[0])
     with pytest.raises(KeyError):
         hoststore.view_from_lists([[np.asarray([[0, num_e + 5]])]], [[t0]], [int(gs.node_ent[0])], gs)   # unknown entity
+
+
+def test_graph_store_relation_ranking():
+    """GraphStore.hot_relations: relation ids of each type column by their frequency over the whole graph_dict (the list the
+    batch-scale gather keeps resident rows for); host logic only (device='cpu')."""
+    from renet_b200 import hoststore, synthetic
+    tkg = synthetic.SyntheticTKG('icews14', seed=3, num_timestamps=12)
+    gs = hoststore.GraphStore(tkg.graph_dict)
+    hot = gs.hot_relations('cpu', n=32)
+    for rev, col in ((False, 'type_s'), (True, 'type_o')):
+        allc = np.concatenate([np.asarray(getattr(g, col), dtype=np.int64) for g in gs.graphs])
+        freq = np.bincount(allc, minlength=gs.num_types)
+        got = hot[rev].numpy()
+        assert len(got) <= 32 and len(set(got.tolist())) == len(got)
+        assert np.all(freq[got] > 0) and np.all(np.diff(freq[got]) <= 0)            # present, most frequent first
+        assert freq[got].min() >= np.sort(freq)[::-1][min(31, np.count_nonzero(freq) - 1)]
+    assert gs.hot_relations('cpu', n=32) is hot                                     # computed once per device
