@@ -388,9 +388,10 @@ rgcn_gather_stream_kernel(const float* __restrict__ X, const int32_t* __restrict
       if (cold) st_bulk_g2s(dst + 800, W + (int64_t)(ix.y & 0xffffu) * 400, 1600, bar);
     }
   };
-  // Everything above read graph structure, weights and the relation ranking only.  From here on the kernel touches what
-  // the previous kernel in the stream produced (the self-loop rows in Hout; layer 2's input rows): with programmatic
-  // stream serialisation (see the launchers) the prologue above overlaps that kernel's tail and launch latency.
+  // Everything above read graph structure, weights and the relation ranking only; from here on the kernel touches what
+  // the previous kernel in the stream produced (the self-loop rows in Hout; layer 2's input rows).  A launcher that uses
+  // programmatic stream serialisation gets the prologue overlapped with that kernel's tail; in plain stream order (what
+  // the library does, see rgcn_fwd.cu) this wait returns immediately.
   asm volatile("griddepcontrol.wait;" ::: "memory");
 #pragma unroll
   for (int k = 0; k < D; ++k)

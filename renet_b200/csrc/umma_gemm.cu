@@ -270,9 +270,6 @@ umma_gemm_packed_kernel(const float* __restrict__ A, const int32_t* __restrict__
                         const float* __restrict__ bias, int64_t M, int N, int K, int n_chunks, int accumulate,
                         int64_t batch_a, int64_t batch_bp, int64_t batch_c, EpiArgs epi, int k_splits, int64_t split_c) {
   extern __shared__ uint8_t smem_raw[];
-  // a kernel launched behind this one with programmatic stream serialisation (the persistent gather) may be scheduled now:
-  // it only reads graph structure and weights until its own griddepcontrol.wait, which returns when this grid has completed
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);     // swizzle atoms need 1024-byte alignment
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
