@@ -59,6 +59,9 @@ def run_synth1m(args, WORKLOAD, METRIC, UNIT, ClockSampler, measured_peak_gbs):
     R2 = 2 * R
     sh = make_shard(torch, N, G, R, Q, SL, 999 + rank, dev)
     E = int(sh['src'].numel())
+    import gc
+    gc.collect()
+    gc.freeze()          # nothing built so far is garbage: keep full collections out of the timed regions
     S = Q * SL
     # ---- graph preprocessing (not timed): CSR by destination, norm, read-out sub-graph
     row_ptr, col_src, col_type, _ = build_csr(sh['dst'], sh['src'], sh['type_s'], N)
