@@ -403,7 +403,10 @@ int renet_prepare_sequences(const int64_t* triplets, int32_t ld, int32_t col_s, 
  * Same arguments as the individual entry points; H1/H2 [N,h] are caller-provided outputs.  With a read-out sub-graph
  * (sub_* = the outputs of renet_readout_subgraph for this batch and type column; all NULL = none) layer 2 runs on it:
  * H2 then holds S compact rows and the GRU reads them through sub_readout.  hot_rel / n_hot: the optional relation ranking
- * of renet_rgcn_gather_hot (NULL / 0 = none), used by both layers. */
+ * of renet_rgcn_gather_hot (NULL / 0 = none), used by both layers.
+ * Stream behaviour: the part of the GRU that does not depend on H2 (weight packing, bias rows, the per-sequence and
+ * per-timestamp projections) is enqueued on a library-owned side stream that forks from `stream` by an event at entry and
+ * joins it by an event before the H2 projection; from the caller's point of view everything is ordered on `stream`. */
 int renet_encode_fwd(const float* ent, const int32_t* node_ent, const int32_t* row_ptr, const int32_t* col_src,
                      const int32_t* col_type, const float* norm,
                      const float* W1, const float* Wloop1, const float* W2, const float* Wloop2,
