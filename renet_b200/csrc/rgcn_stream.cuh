@@ -206,8 +206,9 @@ rgcn_gather_stream_kernel(const float* __restrict__ X, const int32_t* __restrict
     __syncwarp();
     for (int sl = lane; sl < n_hot; sl += 32) {
       const int r = __ldg(hot_rel + sl);
-      slot_of[r] = (uint8_t)(sl + 1);
-      st_bulk_g2s(smem_u32(st_smem + Cfg::kOffHot + sl * 1600), W + (int64_t)r * 400, 1600, hot_bar);
+      const bool ok = r >= 0 && r < R2;                    // an id outside the table is ignored (its slot holds row 0, unused)
+      if (ok) slot_of[r] = (uint8_t)(sl + 1);
+      st_bulk_g2s(smem_u32(st_smem + Cfg::kOffHot + sl * 1600), W + (int64_t)(ok ? r : 0) * 400, 1600, hot_bar);
     }
   }
   // ---- CTA partition: destinations [A, A_next) own 1/gridDim of the edges (node-aligned).  Threads 0..255 look for
