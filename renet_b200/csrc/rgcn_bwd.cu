@@ -53,31 +53,26 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
 }
 
 // dH[u] = dH[u] (loop part, already there when HAS_LOOP) + sum over out-edges of W^T (norm[dst] P[dst]).
-// Tile kernel (rgcn_tile.cuh) for small graphs: 16 source rows per CTA, the out-edge range split evenly over the warps;
-// transposed 2x2 blocks, per-edge scale norm[dst]; the same deterministic atomic-free hand-over as the forward tile kernel
-// (a row a warp starts goes to the tile by plain stores, the tail of a row an earlier warp started to the warp's head slot,
-// heads added in warp = edge order).  At batch scale dH runs through rgcn_gather_stream_kernel<..., BWD = true>.
+// Tile kernel (rgcn_tile.cuh): 16 source rows per CTA, the out-edge range split evenly
+// over the warps; transposed 2x2 blocks, per-edge scale norm[dst].
 template <bool HAS_LOOP>
 __global__ void __launch_bounds__(kTileWarps * 32)
 rgcn_dh_tile_kernel(const float* __restrict__ P, const float* __restrict__ W, const int32_t* __restrict__ t_row_ptr,
                     const int32_t* __restrict__ t_col_dst, const int32_t* __restrict__ t_col_type,
                     const float* __restrict__ norm, float* __restrict__ dH, int N) {
   __shared__ __align__(16) float agg[kTileNodes][200];
-  __shared__ __align__(16) float head[kTileWarps][200];
-  __shared__ int head_mask[kTileNodes];
   __shared__ int s_rp[kTileNodes + 1];
   const int tid = threadIdx.x;
   const int v0 = blockIdx.x * kTileNodes;
   const int nv = min(kTileNodes, N - v0);
-  if (tid < kTileNodes) head_mask[tid] = 0;
+  for (int i = tid; i < kTileNodes * 200; i += kTileWarps * 32) (&agg[0][0])[i] = 0.f;
   if (tid <= nv) s_rp[tid] = __ldg(t_row_ptr + v0 + tid);
   __syncthreads();
-  const TileHeads th{head, head_mask};
-  tile_accumulate<true, false, true, true, true>(agg, s_rp, nv, P, nullptr, W, t_col_dst, t_col_type, norm, th);
+  tile_accumulate<true, false, true>(agg, s_rp, nv, P, nullptr, W, t_col_dst, t_col_type, norm);
   __syncthreads();
   for (int i = tid; i < nv * 100; i += kTileWarps * 32) {
     const int r = i / 100, c = (i % 100) * 2;
-    float2 o = tile_row_sum(agg, th, s_rp, r, c);
+    float2 o = *reinterpret_cast<const float2*>(&agg[r][c]);
     float* op = dH + (int64_t)(v0 + r) * 200 + c;
     if (HAS_LOOP) {
       const float2 l = *reinterpret_cast<const float2*>(op);
